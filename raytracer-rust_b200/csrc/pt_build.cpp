@@ -1,0 +1,481 @@
+// pt_build.cpp — see pt_build.h.  Plain host C++ (no CUDA), compiled into libptcore.so.
+#include "pt_build.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+#include <thread>
+
+namespace pt {
+namespace {
+
+inline const float *tri_ptr(const MeshBuild &m, int64_t i) { return m.tris.data() + i * 12; }
+
+// ------------------------------------------------------------------------------------------------------------
+// Step 1: the reference's median-split build, restated only as far as its shape matters for visibility.
+// bvh.rs:15-76: bounds over the vertices; leaf when n <= 4 or depth >= 25; axis = x if strictly the largest
+// extent, else y if larger than z, else z; sort the index slice by centroid ((v0+v1+v2) * (1/3)) on that axis;
+// split at n/2.  Rust's sort_unstable_by leaves the order of equal keys unspecified (it depends on the std
+// version); this restatement uses a STABLE sort, the same choice the oracle documents (tolerance class T6).
+struct RefCtx {
+  const MeshBuild *m;
+  const float *cen;  // n x 3 centroids
+  uint8_t *dead;
+  std::atomic<int64_t> nodes{0}, leaves{0};
+  std::atomic<int32_t> max_depth{0};
+};
+
+void ref_build(RefCtx &c, int64_t *idx, int64_t n, int depth, bool dead_in, int par_levels) {
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int64_t i = 0; i < n; i++) {
+    const float *t = tri_ptr(*c.m, idx[i]);
+    for (int v = 0; v < 3; v++)
+      for (int a = 0; a < 3; a++) {
+        lo[a] = fminf(lo[a], t[v * 3 + a]);
+        hi[a] = fmaxf(hi[a], t[v * 3 + a]);
+      }
+  }
+  c.nodes.fetch_add(1, std::memory_order_relaxed);
+  int32_t md = c.max_depth.load(std::memory_order_relaxed);
+  while (depth > md && !c.max_depth.compare_exchange_weak(md, depth)) {
+  }
+  // aabb.rs:27-45: on a zero-extent axis t0 == t1, so `t_max <= t_min` holds and the node is never entered
+  const bool flat = (lo[0] == hi[0]) || (lo[1] == hi[1]) || (lo[2] == hi[2]);
+  const bool dead = dead_in || flat;
+  if (n <= 4 || depth >= 25) {
+    c.leaves.fetch_add(1, std::memory_order_relaxed);
+    for (int64_t i = 0; i < n; i++) c.dead[idx[i]] = dead ? 1 : 0;
+    return;
+  }
+  const float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
+  const int axis = (ex > ey && ex > ez) ? 0 : (ey > ez ? 1 : 2);
+  const float *cen = c.cen;
+  std::stable_sort(idx, idx + n, [cen, axis](int64_t a, int64_t b) { return cen[a * 3 + axis] < cen[b * 3 + axis]; });
+  const int64_t mid = n / 2;
+  if (par_levels > 0 && n > (1 << 14)) {
+    std::thread th([&]() { ref_build(c, idx, mid, depth + 1, dead, par_levels - 1); });
+    ref_build(c, idx + mid, n - mid, depth + 1, dead, par_levels - 1);
+    th.join();
+  } else {
+    ref_build(c, idx, mid, depth + 1, dead, 0);
+    ref_build(c, idx + mid, n - mid, depth + 1, dead, 0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Step 2: binned SAH binary BVH over the live triangles.
+struct Box3 {
+  float lo[3], hi[3];
+  void reset() {
+    for (int a = 0; a < 3; a++) {
+      lo[a] = INFINITY;
+      hi[a] = -INFINITY;
+    }
+  }
+  void grow(const Box3 &b) {
+    for (int a = 0; a < 3; a++) {
+      lo[a] = std::min(lo[a], b.lo[a]);
+      hi[a] = std::max(hi[a], b.hi[a]);
+    }
+  }
+  void grow(const float *p) {
+    for (int a = 0; a < 3; a++) {
+      lo[a] = std::min(lo[a], p[a]);
+      hi[a] = std::max(hi[a], p[a]);
+    }
+  }
+  double area() const {
+    const double x = (double)hi[0] - lo[0], y = (double)hi[1] - lo[1], z = (double)hi[2] - lo[2];
+    if (x < 0) return 0.0;
+    return 2.0 * (x * y + y * z + z * x);
+  }
+};
+
+struct B2 {
+  Box3 box;
+  int32_t left = -1, right = -1;  // left < 0: leaf
+  int32_t first = 0, count = 0;   // range in the prim array
+};
+
+struct SahCtx {
+  std::vector<B2> nodes;
+  std::atomic<int32_t> next{0};
+  const Box3 *pbox;   // per live prim
+  const float *pcen;  // per live prim x 3
+  int32_t *prim;      // permutation of live prim ids
+};
+
+constexpr int kBins = 16;
+constexpr int kLeafMax = 3;  // a leaf slot of a wide node addresses at most 3 triangles
+
+int32_t sah_build(SahCtx &c, int32_t first, int32_t count, int par_levels) {
+  const int32_t me = c.next.fetch_add(1);
+  B2 node;
+  node.first = first;
+  node.count = count;
+  node.box.reset();
+  Box3 cb;
+  cb.reset();
+  for (int32_t i = first; i < first + count; i++) {
+    node.box.grow(c.pbox[c.prim[i]]);
+    cb.grow(c.pcen + 3 * (size_t)c.prim[i]);
+  }
+  if (count <= kLeafMax) {
+    c.nodes[me] = node;
+    return me;
+  }
+  int best_axis = -1, best_split = -1;
+  double best_cost = DBL_MAX;
+  for (int a = 0; a < 3; a++) {
+    const float cext = cb.hi[a] - cb.lo[a];
+    if (!(cext > 0.0f)) continue;
+    Box3 bb[kBins];
+    int32_t bn[kBins];
+    for (int b = 0; b < kBins; b++) {
+      bb[b].reset();
+      bn[b] = 0;
+    }
+    const float k = (float)kBins / cext;
+    for (int32_t i = first; i < first + count; i++) {
+      const int32_t p = c.prim[i];
+      int b = (int)((c.pcen[3 * (size_t)p + a] - cb.lo[a]) * k);
+      b = std::min(std::max(b, 0), kBins - 1);
+      bb[b].grow(c.pbox[p]);
+      bn[b]++;
+    }
+    double right_area[kBins];
+    int32_t right_n[kBins];
+    Box3 acc;
+    acc.reset();
+    int32_t cnt = 0;
+    for (int b = kBins - 1; b > 0; b--) {
+      acc.grow(bb[b]);
+      cnt += bn[b];
+      right_area[b] = acc.area();
+      right_n[b] = cnt;
+    }
+    acc.reset();
+    cnt = 0;
+    for (int b = 0; b < kBins - 1; b++) {
+      acc.grow(bb[b]);
+      cnt += bn[b];
+      if (cnt == 0 || right_n[b + 1] == 0) continue;
+      const double cost = acc.area() * cnt + right_area[b + 1] * right_n[b + 1];
+      if (cost < best_cost) {
+        best_cost = cost;
+        best_axis = a;
+        best_split = b + 1;  // bins [0, best_split) go left
+      }
+    }
+  }
+  int32_t mid;
+  if (best_axis < 0) {
+    mid = first + count / 2;  // all centroids coincide
+  } else {
+    const float cext = cb.hi[best_axis] - cb.lo[best_axis];
+    const float k = (float)kBins / cext;
+    const float lo = cb.lo[best_axis];
+    const int a = best_axis, split = best_split;
+    int32_t *b = c.prim + first, *e = c.prim + first + count;
+    int32_t *m = std::partition(b, e, [&](int32_t p) {
+      int bin = (int)((c.pcen[3 * (size_t)p + a] - lo) * k);
+      bin = std::min(std::max(bin, 0), kBins - 1);
+      return bin < split;
+    });
+    mid = first + (int32_t)(m - b);
+    if (mid == first || mid == first + count) mid = first + count / 2;
+  }
+  int32_t l, r;
+  if (par_levels > 0 && count > (1 << 14)) {
+    std::thread th([&]() { l = sah_build(c, first, mid - first, par_levels - 1); });
+    r = sah_build(c, mid, first + count - mid, par_levels - 1);
+    th.join();
+  } else {
+    l = sah_build(c, first, mid - first, 0);
+    r = sah_build(c, mid, first + count - mid, 0);
+  }
+  node.left = l;
+  node.right = r;
+  c.nodes[me] = node;
+  return me;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Step 3: 8-wide collapse + quantisation.
+inline float u2f_host(uint32_t u) {
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+inline uint32_t f2u_host(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  return u;
+}
+
+struct QFrame {
+  float origin[3];
+  int biased_exp[3];
+  double scale[3];
+};
+
+// Frame = node box padded on every side, so that a child plane that coincides with the node's own plane still
+// quantises with slack; the traversal's fused slab arithmetic then cannot cull a box whose face carries the hit.
+QFrame make_frame(const Box3 &box) {
+  QFrame f;
+  for (int a = 0; a < 3; a++) {
+    const float lo = box.lo[a], hi = box.hi[a];
+    const float ext = hi - lo;
+    const float maxabs = std::max(std::fabs(lo), std::fabs(hi));
+    const float pad = ext * (1.0f / 512.0f) + maxabs * 0x1p-20f + 1e-30f;
+    float flo = lo - pad, fhi = hi + pad;
+    if (!(flo < lo)) flo = std::nextafter(lo, -INFINITY);
+    if (!(fhi > hi)) fhi = std::nextafter(hi, INFINITY);
+    const double need = ((double)fhi - (double)flo) / 255.0;
+    int ex;
+    std::frexp(need, &ex);  // need = m * 2^ex, m in [0.5, 1)  =>  2^ex >= need
+    int biased = ex + 127;
+    if (biased < 1) biased = 1;
+    if (biased > 254) throw std::runtime_error("mesh extent too large for the quantised BVH frame");
+    f.origin[a] = flo;
+    f.biased_exp[a] = biased;
+    f.scale[a] = std::ldexp(1.0, biased - 127);
+  }
+  return f;
+}
+
+void collapse(const std::vector<B2> &b2, int32_t root, const int32_t *prim, const int32_t *live_ids, MeshBuild &m) {
+  struct Item {
+    int32_t b2, wide, depth;
+  };
+  std::vector<Item> queue;
+  m.nodes.clear();
+  m.tri48.clear();
+  m.nodes.resize(1);
+  queue.push_back({root, 0, 0});
+  m.wide_depth = 0;
+  for (size_t qi = 0; qi < queue.size(); qi++) {
+    const Item it = queue[qi];
+    m.wide_depth = std::max(m.wide_depth, it.depth);
+    const B2 &n = b2[it.b2];
+    int32_t ch[8];
+    int nch = 0;
+    if (n.left < 0) {
+      ch[nch++] = it.b2;
+    } else {
+      ch[nch++] = n.left;
+      ch[nch++] = n.right;
+    }
+    while (nch < 8) {  // open the inner child with the largest surface area
+      int pick = -1;
+      double pa = -1.0;
+      for (int i = 0; i < nch; i++)
+        if (b2[ch[i]].left >= 0) {
+          const double a = b2[ch[i]].box.area();
+          if (a > pa) {
+            pa = a;
+            pick = i;
+          }
+        }
+      if (pick < 0) break;
+      const int32_t p = ch[pick];
+      ch[pick] = b2[p].left;
+      ch[nch++] = b2[p].right;
+    }
+    // Octant-ordered slots: slot s "lives" at corner (s&1 ? +x : -x, s&2 ? +y : -y, s&4 ? +z : -z); the traversal
+    // visits slot (ray octant) first.  Greedy assignment on dot(child centre - node centre, corner direction).
+    float nc[3];
+    for (int a = 0; a < 3; a++) nc[a] = 0.5f * (n.box.lo[a] + n.box.hi[a]);
+    double cost[8][8];
+    for (int i = 0; i < nch; i++) {
+      const Box3 &cbx = b2[ch[i]].box;
+      for (int s = 0; s < 8; s++) {
+        double d = 0.0;
+        for (int a = 0; a < 3; a++) {
+          const double cc = 0.5 * ((double)cbx.lo[a] + cbx.hi[a]) - nc[a];
+          d += ((s >> a) & 1) ? cc : -cc;
+        }
+        cost[i][s] = d;
+      }
+    }
+    int slot_child[8];
+    for (int s = 0; s < 8; s++) slot_child[s] = -1;
+    bool child_done[8] = {false, false, false, false, false, false, false, false};
+    for (int round = 0; round < nch; round++) {
+      int bi = -1, bs = -1;
+      double bc = -DBL_MAX;
+      for (int i = 0; i < nch; i++) {
+        if (child_done[i]) continue;
+        for (int s = 0; s < 8; s++) {
+          if (slot_child[s] >= 0) continue;
+          if (cost[i][s] > bc) {
+            bc = cost[i][s];
+            bi = i;
+            bs = s;
+          }
+        }
+      }
+      child_done[bi] = true;
+      slot_child[bs] = ch[bi];
+    }
+
+    const QFrame fr = make_frame(n.box);
+    uint8_t meta[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint8_t qlo[3][8], qhi[3][8];
+    for (int a = 0; a < 3; a++)
+      for (int s = 0; s < 8; s++) {
+        qlo[a][s] = 255;
+        qhi[a][s] = 0;
+      }
+    uint32_t imask = 0;
+    const uint32_t child_base = (uint32_t)m.nodes.size();
+    const uint32_t tri_base = (uint32_t)m.tri48.size();
+    int n_inner = 0, tri_off = 0;
+    for (int s = 0; s < 8; s++) {
+      const int32_t c = slot_child[s];
+      if (c < 0) continue;
+      const B2 &cn = b2[c];
+      if (cn.left >= 0) {
+        imask |= 1u << s;
+        meta[s] = (uint8_t)(0x20 | (24 + s));
+        queue.push_back({c, (int32_t)(child_base + n_inner), it.depth + 1});
+        n_inner++;
+      } else {
+        const int cnt = cn.count;
+        const uint32_t unary = cnt == 1 ? 1u : (cnt == 2 ? 3u : 7u);
+        meta[s] = (uint8_t)((unary << 5) | (uint32_t)tri_off);
+        for (int k = 0; k < cnt; k++) {
+          const int32_t orig = live_ids[prim[cn.first + k]];
+          const float *t = tri_ptr(m, orig);
+          Tri48 r;
+          // edge vectors with the reference's own subtraction (bvh.rs:94-95), so precomputing them changes no bit
+          r.t[0] = make_float4(t[0], t[1], t[2], u2f_host((uint32_t)orig));
+          r.t[1] = make_float4(t[3] - t[0], t[4] - t[1], t[5] - t[2], u2f_host((uint32_t)m.order[orig]));
+          r.t[2] = make_float4(t[6] - t[0], t[7] - t[1], t[8] - t[2], 0.0f);
+          m.tri48.push_back(r);
+        }
+        tri_off += cnt;
+      }
+      for (int a = 0; a < 3; a++) {
+        const float clo = cn.box.lo[a], chi = cn.box.hi[a];
+        const double padc = (double)std::max(std::fabs(clo), std::fabs(chi)) * 0x1p-21 + 1e-30;
+        double ql = std::floor(((double)clo - padc - (double)fr.origin[a]) / fr.scale[a]);
+        double qh = std::ceil(((double)chi + padc - (double)fr.origin[a]) / fr.scale[a]);
+        ql = std::min(std::max(ql, 0.0), 255.0);
+        qh = std::min(std::max(qh, 0.0), 255.0);
+        qlo[a][s] = (uint8_t)ql;
+        qhi[a][s] = (uint8_t)qh;
+      }
+    }
+    m.nodes.resize(child_base + n_inner);
+
+    auto pack4 = [](const uint8_t *b) -> float {
+      return u2f_host((uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24));
+    };
+    Node8 out;
+    const uint32_t ebits = (uint32_t)fr.biased_exp[0] | ((uint32_t)fr.biased_exp[1] << 8) |
+                           ((uint32_t)fr.biased_exp[2] << 16) | (imask << 24);
+    out.q[0] = make_float4(fr.origin[0], fr.origin[1], fr.origin[2], u2f_host(ebits));
+    out.q[1] = make_float4(u2f_host(child_base), u2f_host(tri_base), pack4(meta), pack4(meta + 4));
+    out.q[2] = make_float4(pack4(qlo[0]), pack4(qlo[0] + 4), pack4(qlo[1]), pack4(qlo[1] + 4));
+    out.q[3] = make_float4(pack4(qlo[2]), pack4(qlo[2] + 4), pack4(qhi[0]), pack4(qhi[0] + 4));
+    out.q[4] = make_float4(pack4(qhi[1]), pack4(qhi[1] + 4), pack4(qhi[2]), pack4(qhi[2] + 4));
+    m.nodes[it.wide] = out;
+  }
+  (void)f2u_host;
+}
+
+}  // namespace
+
+void build_mesh(MeshBuild &m, int threads) {
+  const int64_t n = m.n;
+  if (n <= 0) throw std::runtime_error("mesh without triangles");
+  if (n > (int64_t)0x7fffffff) throw std::runtime_error("mesh too large");
+  int nt = threads > 0 ? threads : (int)std::max(1u, std::thread::hardware_concurrency());
+  int par_levels = 0;
+  while ((1 << par_levels) < nt && par_levels < 6) par_levels++;
+
+  // ---- step 1
+  std::vector<float> cen((size_t)n * 3);
+  for (int64_t i = 0; i < n; i++) {
+    const float *t = tri_ptr(m, i);
+    for (int a = 0; a < 3; a++) cen[(size_t)i * 3 + a] = ((t[a] + t[3 + a]) + t[6 + a]) * (1.0f / 3.0f);  // bvh.rs:46
+  }
+  m.dead.assign((size_t)n, 0);
+  m.order.assign((size_t)n, 0);
+  {
+    std::vector<int64_t> idx((size_t)n);
+    for (int64_t i = 0; i < n; i++) idx[(size_t)i] = i;
+    RefCtx rc;
+    rc.m = &m;
+    rc.cen = cen.data();
+    rc.dead = m.dead.data();
+    ref_build(rc, idx.data(), n, 0, false, par_levels);
+    m.ref_nodes = rc.nodes.load();
+    m.ref_leaves = rc.leaves.load();
+    m.ref_depth = rc.max_depth.load();
+    for (int64_t pos = 0; pos < n; pos++) m.order[(size_t)idx[(size_t)pos]] = (int32_t)pos;
+  }
+
+  // ---- normals by original index
+  m.normals.resize((size_t)n);
+  for (int64_t i = 0; i < n; i++) {
+    const float *t = tri_ptr(m, i);
+    m.normals[(size_t)i] = make_float4(t[9], t[10], t[11], 0.0f);
+  }
+
+  // ---- step 2
+  std::vector<int32_t> live_ids;
+  live_ids.reserve((size_t)n);
+  for (int64_t i = 0; i < n; i++)
+    if (!m.dead[(size_t)i]) live_ids.push_back((int32_t)i);
+  m.live = (int64_t)live_ids.size();
+  m.nodes.clear();
+  m.tri48.clear();
+  m.wide_depth = 0;
+  if (live_ids.empty()) {
+    // every triangle is unreachable in the reference: an empty root (no child bits) never reports a hit
+    Node8 empty;
+    const uint32_t e = 127u | (127u << 8) | (127u << 16);
+    empty.q[0] = make_float4(0, 0, 0, u2f_host(e));
+    empty.q[1] = make_float4(u2f_host(1u), u2f_host(0u), u2f_host(0u), u2f_host(0u));
+    const float inv = u2f_host(0xffffffffu), zero = u2f_host(0u);
+    empty.q[2] = make_float4(inv, inv, inv, inv);
+    empty.q[3] = make_float4(inv, inv, zero, zero);
+    empty.q[4] = make_float4(zero, zero, zero, zero);
+    m.nodes.push_back(empty);
+    Tri48 z;
+    z.t[0] = z.t[1] = z.t[2] = make_float4(0, 0, 0, 0);
+    m.tri48.push_back(z);  // keep the buffer non-empty
+    m.built = true;
+    return;
+  }
+  const size_t nl = live_ids.size();
+  std::vector<Box3> pbox(nl);
+  std::vector<float> pcen(nl * 3);
+  std::vector<int32_t> prim(nl);
+  for (size_t i = 0; i < nl; i++) {
+    const float *t = tri_ptr(m, live_ids[i]);
+    pbox[i].reset();
+    pbox[i].grow(t);
+    pbox[i].grow(t + 3);
+    pbox[i].grow(t + 6);
+    for (int a = 0; a < 3; a++) pcen[i * 3 + a] = 0.5f * (pbox[i].lo[a] + pbox[i].hi[a]);
+    prim[i] = (int32_t)i;
+  }
+  SahCtx sc;
+  sc.nodes.resize(2 * nl);
+  sc.pbox = pbox.data();
+  sc.pcen = pcen.data();
+  sc.prim = prim.data();
+  const int32_t root = sah_build(sc, 0, (int32_t)nl, par_levels);
+
+  // ---- step 3
+  collapse(sc.nodes, root, prim.data(), live_ids.data(), m);
+  m.built = true;
+}
+
+}  // namespace pt

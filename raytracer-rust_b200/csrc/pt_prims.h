@@ -1,0 +1,181 @@
+// pt_prims.h — closest hit over the object list: HittableList::hit (src/hittable.rs:46-57) and the `hit` of every
+// primitive, with the reference's interval conventions (open for sphere / plane / quad / triangle, closed world-t
+// recheck for cube and mesh) and operation order.
+#pragma once
+#include "pt_bvh8.h"
+#include "pt_math.h"
+#include "pt_types.h"
+
+namespace pt {
+
+// hittable.rs:19-26
+PT_HD void set_face_normal(Hit &h, V3 ray_d, V3 outward) {
+  bool front = dot(ray_d, outward) < 0.0f;
+  V3 n = front ? outward : -outward;
+  h.front_face = front ? 1 : 0;
+  h.nx = n.x;
+  h.ny = n.y;
+  h.nz = n.z;
+}
+PT_HD void set_pos(Hit &h, V3 p) {
+  h.px = p.x;
+  h.py = p.y;
+  h.pz = p.z;
+}
+
+// src/objects/sphere.rs:15-53
+PT_HD bool hit_sphere(const float *f, const Ray &ray, float t_min, float t_max, Hit &h) {
+  const V3 center = v3(f[0], f[1], f[2]);
+  const float radius = f[3];
+  const V3 oc = ray.o - center;
+  const float a = dot(ray.d, ray.d);
+  const float half_b = dot(oc, ray.d);
+  const float c = dot(oc, oc) - radius * radius;
+  const float disc = half_b * half_b - a * c;
+  if (disc < 0.0f) return false;
+  const float sqrtd = sqrtf(disc);
+  float root = (-half_b - sqrtd) / a;
+  if (root <= t_min || root >= t_max) {
+    root = (-half_b + sqrtd) / a;
+    if (root <= t_min || root >= t_max) return false;
+  }
+  h.t = root;
+  const V3 p = ray_at(ray, root);
+  set_pos(h, p);
+  const V3 outward = (p - center) / radius;  // vec3.rs:117-129 would panic for |radius| < 1e-4; the device divides
+  set_face_normal(h, ray.d, outward);
+  return true;
+}
+
+// src/objects/plane.rs:26-56
+PT_HD bool hit_plane(const float *f, const Ray &ray, float t_min, float t_max, Hit &h) {
+  const V3 p1 = v3(f[0], f[1], f[2]), n = v3(f[3], f[4], f[5]);
+  const float denom = dot(n, ray.d);
+  if (fabsf(denom) < kEps) return false;
+  const float t = dot(n, p1 - ray.o) / denom;
+  if (t <= t_min || t >= t_max) return false;
+  h.t = t;
+  set_pos(h, ray_at(ray, t));
+  set_face_normal(h, ray.d, n);
+  return true;
+}
+
+// src/tungsten/objects/quad.rs:83-132
+PT_HD bool hit_quad(const float *f, const Ray &ray, float t_min, float t_max, Hit &h) {
+  const V3 base = v3(f[0], f[1], f[2]), e0 = v3(f[3], f[4], f[5]), e1 = v3(f[6], f[7], f[8]), n = v3(f[9], f[10], f[11]);
+  const float d = f[12], inv0 = f[13], inv1 = f[14];
+  const float denom = dot(n, ray.d);
+  if (fabsf(denom) < kEps) return false;
+  const float t = (d - dot(n, ray.o)) / denom;
+  if (t <= t_min || t >= t_max) return false;
+  const V3 p = ray_at(ray, t);
+  const V3 v = p - base;
+  const float l0 = dot(v, e0) * inv0;
+  const float l1 = dot(v, e1) * inv1;
+  const float lo = -kEps, hi = 1.0f + kEps;
+  if (!((lo <= l0 && l0 <= hi) && (lo <= l1 && l1 <= hi))) return false;
+  h.t = t;
+  set_pos(h, p);
+  set_face_normal(h, ray.d, n);
+  return true;
+}
+
+// src/objects/cube.rs:59-158.  f[0..15] = world_to_object, f[16..31] = object_to_world.
+PT_HD bool hit_cube(const float *f, const Ray &ray, float t_min, float t_max, Hit &h) {
+  const float *w2o = f, *o2w = f + 16;
+  const V3 o = mat_point(w2o, ray.o);
+  const V3 d = mat_vector(w2o, ray.d);  // not renormalised (cube.rs:70-83)
+  const float ix = 1.0f / d.x, iy = 1.0f / d.y, iz = 1.0f / d.z;
+  const float t1x = (-0.5f - o.x) * ix, t2x = (0.5f - o.x) * ix;
+  const float t1y = (-0.5f - o.y) * iy, t2y = (0.5f - o.y) * iy;
+  const float t1z = (-0.5f - o.z) * iz, t2z = (0.5f - o.z) * iz;
+  const float t_enter = fmaxf(fminf(t1x, t2x), fmaxf(fminf(t1y, t2y), fminf(t1z, t2z)));
+  const float t_exit = fminf(fmaxf(t1x, t2x), fminf(fmaxf(t1y, t2y), fmaxf(t1z, t2z)));
+  if (t_exit < t_enter || t_exit <= 0.0f) return false;
+  const float t_obj = t_enter > 0.0f ? t_enter : t_exit;
+  if (t_obj >= t_max || t_obj <= t_min || t_obj < kEps) return false;
+  const V3 p = o + d * t_obj;
+  V3 n = v3(0, 0, 0);
+  const float ax = fabsf(p.x), ay = fabsf(p.y), az = fabsf(p.z);
+  const float tol = 1e-4f;
+  if (fabsf(ax - 0.5f) < tol) n.x = signum(p.x);
+  else if (fabsf(ay - 0.5f) < tol) n.y = signum(p.y);
+  else if (fabsf(az - 0.5f) < tol) n.z = signum(p.z);
+  else if (ax > ay && ax > az) n.x = signum(p.x);
+  else if (ay > az) n.y = signum(p.y);
+  else n.z = signum(p.z);
+  {  // glam normalize_or_zero
+    const float rcp = 1.0f / sqrtf(dot(n, n));
+    if (!isinf_f(rcp) && !isnan_f(rcp) && rcp > 0.0f) n = n * rcp;
+    else n = v3(0, 0, 0);
+  }
+  const V3 pw = mat_point(o2w, p);
+  const V3 nw = normalized(mat_t_vector(w2o, n));
+  if (dot(pw - ray.o, ray.d) < 0.0f) return false;
+  const float t_world = dot(pw - ray.o, ray.d);
+  if (t_world < t_min || t_world > t_max) return false;  // closed interval (cube.rs:150)
+  h.t = t_world;
+  set_pos(h, pw);
+  set_face_normal(h, ray.d, nw);
+  return true;
+}
+
+// src/mesh/mesh_object.rs:262-329
+template <bool COUNT>
+PT_HD bool hit_mesh(const float *f, const DMesh &mesh, const Ray &ray, float t_min, float t_max, Hit &h,
+                    TraversalCounters *ctr) {
+  const float *w2o = f, *o2w = f + 16;
+  const V3 o = mat_point(w2o, ray.o);
+  const V3 d_raw = mat_vector(w2o, ray.d);
+  const V3 d = normalized(normalized(d_raw));  // normalised at mesh_object.rs:287 and again by Ray::new (ray.rs:15)
+  if (COUNT) ctr->mesh_rays++;
+  MeshHit mh;
+  // the BVH is queried with the WORLD t bounds (mesh_object.rs:289-291)
+  if (!bvh8_closest<COUNT>(mesh, o, d, t_min, t_max, mh, ctr)) return false;
+  const V3 p_obj = o + d * mh.t;  // ray.at(t), bvh.rs:119
+  const float4 nq = ldg4(mesh.normals + mh.tri);
+  V3 n_obj = v3(nq.x, nq.y, nq.z);
+  if (!(dot(d, n_obj) < 0.0f)) n_obj = -n_obj;  // bvh.rs:120-126
+  const V3 pw = mat_point(o2w, p_obj);
+  const V3 nw = normalized(mat_t_vector(w2o, n_obj));
+  const float t_world = mh.t * length(d_raw) / length(ray.d);  // mesh_object.rs:312-314
+  if (t_world < t_min || t_world > t_max) return false;          // closed (mesh_object.rs:316)
+  h.t = t_world;
+  h.triangle = (int32_t)mh.tri;
+  set_pos(h, pw);
+  set_face_normal(h, ray.d, nw);
+  return true;
+}
+
+// HittableList::hit (hittable.rs:46-57): linear scan in insertion order with a shrinking t_max; each primitive's
+// own interval test decides what happens on equal t.
+template <bool COUNT>
+PT_HD bool scene_hit(const DScene &sc, const Ray &ray, float t_min, float t_max, Hit &best, TraversalCounters *ctr) {
+  float closest = t_max;
+  bool any = false;
+  best.object = -1;
+  best.triangle = -1;
+  best.material = -1;
+  for (int i = 0; i < sc.n_objects; i++) {
+    const DObject *ob = sc.objects + i;
+    const int type = ob->type;
+    Hit tmp;
+    tmp.triangle = -1;
+    bool hit;
+    if (type == OBJ_SPHERE) hit = hit_sphere(ob->f, ray, t_min, closest, tmp);
+    else if (type == OBJ_QUAD) hit = hit_quad(ob->f, ray, t_min, closest, tmp);
+    else if (type == OBJ_CUBE) hit = hit_cube(ob->f, ray, t_min, closest, tmp);
+    else if (type == OBJ_MESH) hit = hit_mesh<COUNT>(ob->f, sc.meshes[ob->mesh], ray, t_min, closest, tmp, ctr);
+    else hit = hit_plane(ob->f, ray, t_min, closest, tmp);
+    if (hit) {
+      any = true;
+      closest = tmp.t;
+      best = tmp;
+      best.object = i;
+      best.material = ob->material;
+    }
+  }
+  return any;
+}
+
+}  // namespace pt

@@ -1,0 +1,925 @@
+// ptcore.cu — the B200 path-tracing core: wavefront kernels for sm_100a + the C ABI of include/ptcore.h.
+//
+// Replaces the body of render_scene (src/renderer.rs:87-106 of the reference) and everything trace_ray
+// (renderer.rs:19-65) calls.  trace_ray's recursion  L = Le + f * trace(next)  is unrolled into a wavefront:
+//
+//   generate : path index -> (pixel, sample) -> Philox jitter -> Camera::get_ray          (renderer.rs:96-99)
+//   extend   : closest hit of every live ray (HittableList::hit + primitives + BVH)        (renderer.rs:24)
+//   shade    : miss -> sky; hit -> emitted + Material::scatter; throughput update;         (renderer.rs:26-63)
+//              survivors are compacted into the other ray buffer (warp ballot + one atomic per warp)
+//   advance  : one thread; tops the survivor buffer up with fresh camera paths (path regeneration) so the
+//              wavefront stays full although most paths leave after a few segments
+//
+// Only Emissive surfaces and the sky carry radiance and both end the path (EmissiveLight::scatter is None), so a
+// path contributes beta * Le exactly once, when it terminates: one float RED triple per path into the film.
+// extend runs persistent warps that fetch 32 rays at a time from a device-side counter; every kernel reads its
+// item count from device memory, so the host enqueues iterations without synchronising and only polls a
+// pinned copy of the control block every few iterations.
+//
+// There is no CPU fallback in this library: without a CUDA device commit / render / intersect return PTC_E_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <string>
+#include <vector>
+
+#include "../../include/ptcore.h"
+#include "pt_bsdf.h"
+#include "pt_philox.h"
+#include "pt_prims.h"
+#include "pt_scene_host.h"
+
+using namespace pt;
+
+namespace {
+
+thread_local std::string g_err;
+
+struct CudaError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+#define CK(call)                                                                                      \
+  do {                                                                                                \
+    cudaError_t e_ = (call);                                                                          \
+    if (e_ != cudaSuccess)                                                                            \
+      throw CudaError(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------------------
+// Device-side control block of one render (lives in device memory, mirrored to pinned host memory for polling)
+struct Ctl {
+  unsigned long long next_path;   // next camera path index to start
+  unsigned long long total_paths; // path index space of this call (padded tiles x samples)
+  unsigned long long rays;        // extend items so far = trace_ray calls with depth > 0
+  unsigned long long nodes, tris, mesh_rays;  // PTC_FLAG_COUNTERS
+  uint32_t n_cur;        // rays in the current buffer
+  uint32_t n_next;       // survivors appended to the other buffer by shade
+  uint32_t work_extend;  // dynamic fetch cursor of the persistent extend warps
+  uint32_t gen_count;    // camera paths generate has to start this iteration
+  unsigned long long gen_first_path;
+  uint32_t iterations;
+  uint32_t done;
+};
+
+struct RenderParams {
+  DCamera cam;
+  int32_t width, height;
+  int32_t max_depth;
+  int32_t sample_begin, n_samples;
+  int32_t tiles_x, n_my_tiles, tile_mod, tile_rem;
+  uint32_t pool;
+  uint64_t seed;
+};
+
+struct Buffers {
+  float4 *ray_o[2];  // origin.xyz, pixel index
+  float4 *ray_d[2];  // direction.xyz, sample index
+  float4 *beta[2];   // throughput.rgb, bounce (segments already traced)
+  float4 *hit0;      // position.xyz, t
+  float4 *hit1;      // normal.xyz, [hit<<31 | front_face<<30 | material]
+};
+
+constexpr uint32_t kHitBit = 0x80000000u, kFrontBit = 0x40000000u, kMatMask = 0x3fffffffu;
+
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_advance(Ctl *ctl, uint32_t pool) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (ctl->n_cur != 0) {
+    ctl->rays += ctl->n_cur;
+    ctl->iterations++;
+  }
+  const uint32_t n = ctl->n_next;
+  const unsigned long long remaining = ctl->total_paths - ctl->next_path;
+  const unsigned long long space = pool - n;
+  const uint32_t g = (uint32_t)(remaining < space ? remaining : space);
+  ctl->gen_first_path = ctl->next_path;
+  ctl->gen_count = g;
+  ctl->next_path += g;
+  ctl->n_cur = n;  // generate appends the valid camera rays behind the survivors
+  ctl->n_next = 0;
+  ctl->work_extend = 0;
+  ctl->done = (g == 0 && n == 0) ? 1u : 0u;
+}
+
+// path index -> pixel/sample.  Paths are ordered sample-major, then by this rank's 32x32 tiles, then row-major inside
+// a tile, so a warp starts 32 horizontally adjacent pixels of one sample (coherent primary rays, distinct film
+// addresses).  Pixels of partial border tiles that fall outside the image start no path.
+__global__ void __launch_bounds__(256) k_generate(Ctl *ctl, RenderParams rp, Buffers b, int dst) {
+  const uint32_t count = ctl->gen_count;
+  const unsigned long long first = ctl->gen_first_path;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned long long per_sample = (unsigned long long)rp.n_my_tiles * 1024ull;
+  for (uint32_t base = warp_id * 32u; base < count; base += warps_total * 32u) {
+    const uint32_t j = base + lane;
+    bool valid = j < count;
+    uint32_t pixel = 0, sample = 0;
+    int x = 0, y = 0;
+    if (valid) {
+      const unsigned long long p = first + j;
+      const uint32_t s = (uint32_t)(p / per_sample);
+      const uint32_t r = (uint32_t)(p - (unsigned long long)s * per_sample);
+      const uint32_t local_tile = r >> 10, in_tile = r & 1023u;
+      const uint32_t tile = local_tile * (uint32_t)rp.tile_mod + (uint32_t)rp.tile_rem;
+      x = (int)((tile % (uint32_t)rp.tiles_x) * 32u + (in_tile & 31u));
+      y = (int)((tile / (uint32_t)rp.tiles_x) * 32u + (in_tile >> 5));
+      valid = x < rp.width && y < rp.height;
+      pixel = (uint32_t)(y * rp.width + x);
+      sample = (uint32_t)rp.sample_begin + s;
+    }
+    const uint32_t mask = __ballot_sync(0xffffffffu, valid);
+    if (mask == 0u) continue;
+    uint32_t slot0 = 0;
+    if (lane == 0) slot0 = atomicAdd(&ctl->n_cur, (uint32_t)__popc(mask));
+    slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+    if (valid) {
+      const uint32_t slot = slot0 + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+      const Uniforms4 jit = philox_uniforms(rp.seed, pixel, sample, 0xffffffffu, 0u);
+      const float u = ((float)x + jit.u[0]) / (float)rp.width;   // renderer.rs:96
+      const float v = ((float)y + jit.u[1]) / (float)rp.height;  // renderer.rs:97
+      const Ray ray = camera_get_ray(rp.cam, u, v);
+      b.ray_o[dst][slot] = make_float4(ray.o.x, ray.o.y, ray.o.z, u2f(pixel));
+      b.ray_d[dst][slot] = make_float4(ray.d.x, ray.d.y, ray.d.z, u2f(sample));
+      b.beta[dst][slot] = make_float4(1.0f, 1.0f, 1.0f, u2f(0u));
+    }
+  }
+}
+
+// extend: persistent warps, 32 rays per fetch.
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_extend(Ctl *ctl, DScene sc, Buffers b, int src) {
+  const uint32_t n = ctl->n_cur;
+  const uint32_t lane = threadIdx.x & 31u;
+  TraversalCounters tc{0u, 0u, 0u};
+  for (;;) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&ctl->work_extend, 32u);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= n) break;
+    const uint32_t i = base + lane;
+    if (i < n) {
+      const float4 o4 = b.ray_o[src][i], d4 = b.ray_d[src][i];
+      const Ray ray{v3(o4.x, o4.y, o4.z), v3(d4.x, d4.y, d4.z)};
+      Hit h;
+      const bool hit = scene_hit<COUNT>(sc, ray, kEps, INFINITY, h, &tc);  // renderer.rs:24
+      if (hit) {
+        b.hit0[i] = make_float4(h.px, h.py, h.pz, h.t);
+        b.hit1[i] = make_float4(h.nx, h.ny, h.nz, u2f(kHitBit | (h.front_face ? kFrontBit : 0u) | ((uint32_t)h.material & kMatMask)));
+      } else {
+        b.hit1[i] = make_float4(0.0f, 0.0f, 0.0f, u2f(0u));
+      }
+    }
+    __syncwarp();
+  }
+  if (COUNT) {
+    atomicAdd(&ctl->nodes, (unsigned long long)tc.nodes);
+    atomicAdd(&ctl->tris, (unsigned long long)tc.tris);
+    atomicAdd(&ctl->mesh_rays, (unsigned long long)tc.mesh_rays);
+  }
+}
+
+// shade: emitted + scatter (renderer.rs:26-36) or sky (renderer.rs:38-63); compacts survivors into buffer `dst`.
+__global__ void __launch_bounds__(256) k_shade(Ctl *ctl, DScene sc, RenderParams rp, Buffers b, int src, int dst, float *accum) {
+  const uint32_t n = ctl->n_cur;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  for (uint32_t base = warp_id * 32u; base < n; base += warps_total * 32u) {
+    const uint32_t i = base + lane;
+    bool alive = false;
+    float4 no, nd, nb;
+    if (i < n) {
+      const float4 o4 = b.ray_o[src][i], d4 = b.ray_d[src][i], b4 = b.beta[src][i];
+      const float4 h1 = b.hit1[i];
+      const uint32_t pixel = f2u(o4.w), sample = f2u(d4.w), bounce = f2u(b4.w);
+      const uint32_t bits = f2u(h1.w);
+      const V3 beta = v3(b4.x, b4.y, b4.z);
+      const V3 ray_d = v3(d4.x, d4.y, d4.z);
+      V3 radiance = v3(0, 0, 0);
+      bool add = false;
+      if (!(bits & kHitBit)) {
+        radiance = beta * sky_color(sc, ray_d);
+        add = true;
+      } else {
+        const float4 h0 = b.hit0[i];
+        const DMaterial m = sc.materials[bits & kMatMask];
+        const V3 e = mat_emitted(m);
+        if (e.x != 0.0f || e.y != 0.0f || e.z != 0.0f) {
+          radiance = beta * e;
+          add = true;
+        }
+        const Uniforms4 u = philox_uniforms(rp.seed, pixel, sample, bounce, 0u);
+        Ray sc_ray;
+        V3 att;
+        if (mat_scatter(m, ray_d, v3(h0.x, h0.y, h0.z), v3(h1.x, h1.y, h1.z), (bits & kFrontBit) != 0u, u.u, sc_ray, att)) {
+          // trace_ray(scattered, depth - 1): depth 0 returns black (renderer.rs:20-22)
+          if (bounce + 1u < (uint32_t)rp.max_depth) {
+            alive = true;
+            const V3 nbeta = beta * att;
+            no = make_float4(sc_ray.o.x, sc_ray.o.y, sc_ray.o.z, o4.w);
+            nd = make_float4(sc_ray.d.x, sc_ray.d.y, sc_ray.d.z, d4.w);
+            nb = make_float4(nbeta.x, nbeta.y, nbeta.z, u2f(bounce + 1u));
+          }
+        }
+      }
+      if (add) {
+        float *px = accum + (size_t)pixel * 3;
+        atomicAdd(px + 0, radiance.x);
+        atomicAdd(px + 1, radiance.y);
+        atomicAdd(px + 2, radiance.z);
+      }
+    }
+    const uint32_t mask = __ballot_sync(0xffffffffu, alive);
+    if (mask != 0u) {
+      uint32_t slot0 = 0;
+      if (lane == 0) slot0 = atomicAdd(&ctl->n_next, (uint32_t)__popc(mask));
+      slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+      if (alive) {
+        const uint32_t slot = slot0 + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+        b.ray_o[dst][slot] = no;
+        b.ray_d[dst][slot] = nd;
+        b.beta[dst][slot] = nb;
+      }
+    }
+  }
+}
+
+// out = rgb * scale (renderer.rs:103)
+__global__ void k_scale(const float *in, float *out, size_t n, float scale) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i] * scale;
+}
+// renderer.rs:112-120 + color.rs:87-93
+__global__ void k_resolve(const float *rgb, size_t n_pixels, float scale, uint32_t *out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_pixels) out[i] = resolve_pixel(rgb[i * 3] * scale, rgb[i * 3 + 1] * scale, rgb[i * 3 + 2] * scale);
+}
+
+// ---- parity hooks: the same device functions, driven by caller-provided inputs ------------------------------
+__global__ void k_intersect(DScene sc, const float *o, const float *d, size_t n, float t_min, float t_max, ptc_hit *out,
+                            unsigned long long *counters) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  TraversalCounters tc{0u, 0u, 0u};
+  if (i < n) {
+    const Ray ray{v3(o[i * 3], o[i * 3 + 1], o[i * 3 + 2]), v3(d[i * 3], d[i * 3 + 1], d[i * 3 + 2])};
+    Hit h;
+    ptc_hit r;
+    memset(&r, 0, sizeof(r));
+    if (scene_hit<true>(sc, ray, t_min, t_max, h, &tc)) {
+      r.object = h.object;
+      r.triangle = h.triangle;
+      r.t = h.t;
+      r.position[0] = h.px, r.position[1] = h.py, r.position[2] = h.pz;
+      r.normal[0] = h.nx, r.normal[1] = h.ny, r.normal[2] = h.nz;
+      r.front_face = h.front_face;
+      r.material = h.material;
+    } else {
+      r.object = -1, r.triangle = -1, r.material = -1;
+    }
+    out[i] = r;
+  }
+  if (counters) {
+    atomicAdd(counters + 0, (unsigned long long)tc.nodes);
+    atomicAdd(counters + 1, (unsigned long long)tc.tris);
+    atomicAdd(counters + 2, (unsigned long long)tc.mesh_rays);
+  }
+}
+
+__global__ void k_primary_rays(RenderParams rp, uint32_t sample, float *out_o, float *out_d) {
+  const uint32_t pixel = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pixel >= (uint32_t)(rp.width * rp.height)) return;
+  const int x = (int)(pixel % (uint32_t)rp.width), y = (int)(pixel / (uint32_t)rp.width);
+  const Uniforms4 jit = philox_uniforms(rp.seed, pixel, sample, 0xffffffffu, 0u);
+  const float u = ((float)x + jit.u[0]) / (float)rp.width;
+  const float v = ((float)y + jit.u[1]) / (float)rp.height;
+  const Ray ray = camera_get_ray(rp.cam, u, v);
+  out_o[pixel * 3 + 0] = ray.o.x, out_o[pixel * 3 + 1] = ray.o.y, out_o[pixel * 3 + 2] = ray.o.z;
+  out_d[pixel * 3 + 0] = ray.d.x, out_d[pixel * 3 + 1] = ray.d.y, out_d[pixel * 3 + 2] = ray.d.z;
+}
+
+__global__ void k_scatter(DMaterial m, const float *dirs, const float *pos, const float *nrm, const int32_t *front,
+                          const float *u4, size_t n, int32_t *scattered, float *out_o, float *out_d, float *att_out,
+                          float *emitted) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Ray sr{v3(0, 0, 0), v3(0, 0, 0)};
+  V3 att = v3(0, 0, 0);
+  const V3 e = mat_emitted(m);
+  const float u[4] = {u4[i * 4], u4[i * 4 + 1], u4[i * 4 + 2], u4[i * 4 + 3]};
+  const bool ok = mat_scatter(m, v3(dirs[i * 3], dirs[i * 3 + 1], dirs[i * 3 + 2]), v3(pos[i * 3], pos[i * 3 + 1], pos[i * 3 + 2]),
+                              v3(nrm[i * 3], nrm[i * 3 + 1], nrm[i * 3 + 2]), front[i] != 0, u, sr, att);
+  scattered[i] = ok ? 1 : 0;
+  out_o[i * 3] = sr.o.x, out_o[i * 3 + 1] = sr.o.y, out_o[i * 3 + 2] = sr.o.z;
+  out_d[i * 3] = sr.d.x, out_d[i * 3 + 1] = sr.d.y, out_d[i * 3 + 2] = sr.d.z;
+  att_out[i * 3] = att.x, att_out[i * 3 + 1] = att.y, att_out[i * 3 + 2] = att.z;
+  emitted[i * 3] = e.x, emitted[i * 3 + 1] = e.y, emitted[i * 3 + 2] = e.z;
+}
+
+__global__ void k_philox(U4 c, uint32_t k0, uint32_t k1, uint32_t *out) {
+  const U4 r = philox4x32_10(c, k0, k1);
+  out[0] = r.x, out[1] = r.y, out[2] = r.z, out[3] = r.w;
+}
+
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  void alloc(size_t count) {
+    release();
+    if (count == 0) count = 1;
+    CK(cudaMalloc(&p, count * sizeof(T)));
+    n = count;
+  }
+  void upload(const T *src, size_t count) {
+    alloc(count);
+    if (count) CK(cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice));
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  ~DevBuf() { release(); }
+  DevBuf() = default;
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+};
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------------
+struct ptc_scene {
+  HostScene hs;
+  bool committed = false;
+  int device = -1;
+  int sm_count = 0;
+  DevBuf<DObject> d_objects;
+  DevBuf<DMaterial> d_materials;
+  DevBuf<DMesh> d_meshes;
+  DevBuf<float> d_sky;
+  std::vector<std::unique_ptr<DevBuf<float4>>> mesh_bufs;
+  DScene ds;
+
+  // render workspace
+  uint32_t pool = 0;
+  DevBuf<float4> w_ray_o[2], w_ray_d[2], w_beta[2], w_hit0, w_hit1;
+  DevBuf<Ctl> d_ctl;
+  Ctl *h_ctl = nullptr;  // pinned ring
+  static constexpr int kRing = 4;
+  cudaEvent_t ring_ev[kRing] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t own_stream = nullptr;
+  std::vector<cudaEvent_t> timing_events;
+
+  ~ptc_scene() {
+    if (device >= 0) cudaSetDevice(device);
+    if (h_ctl) cudaFreeHost(h_ctl);
+    for (auto &e : ring_ev)
+      if (e) cudaEventDestroy(e);
+    for (auto &e : timing_events) cudaEventDestroy(e);
+    if (own_stream) cudaStreamDestroy(own_stream);
+  }
+};
+
+namespace {
+
+void ensure_workspace(ptc_scene *s, uint32_t pool) {
+  if (s->pool == pool && s->h_ctl) return;
+  for (int k = 0; k < 2; k++) {
+    s->w_ray_o[k].alloc(pool);
+    s->w_ray_d[k].alloc(pool);
+    s->w_beta[k].alloc(pool);
+  }
+  s->w_hit0.alloc(pool);
+  s->w_hit1.alloc(pool);
+  s->d_ctl.alloc(1);
+  if (!s->h_ctl) {
+    CK(cudaMallocHost(&s->h_ctl, sizeof(Ctl) * ptc_scene::kRing));
+    for (auto &e : s->ring_ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  s->pool = pool;
+}
+
+Buffers buffers_of(ptc_scene *s) {
+  Buffers b;
+  for (int k = 0; k < 2; k++) {
+    b.ray_o[k] = s->w_ray_o[k].p;
+    b.ray_d[k] = s->w_ray_d[k].p;
+    b.beta[k] = s->w_beta[k].p;
+  }
+  b.hit0 = s->w_hit0.p;
+  b.hit1 = s->w_hit1.p;
+  return b;
+}
+
+void require_committed(const ptc_scene *s) {
+  if (!s) throw std::invalid_argument("null scene");
+  if (!s->committed) throw std::logic_error("scene not committed (call ptc_scene_commit first)");
+}
+
+// the wavefront loop; adds radiance sums into d_accum on `stream`
+void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_settings *st, float *d_accum,
+                       cudaStream_t stream, ptc_stats *stats) {
+  require_committed(s);
+  if (!cam || !st || !d_accum) throw std::invalid_argument("null argument");
+  if (st->width <= 0 || st->height <= 0 || st->spp <= 0) throw std::invalid_argument("bad render settings");
+  if ((int64_t)st->width * st->height > (int64_t)0x3fffffff) throw std::invalid_argument("image too large");
+  CK(cudaSetDevice(s->device));
+  int s_begin = st->sample_begin, s_end = st->sample_end;
+  if (s_begin == 0 && s_end == 0) s_end = st->spp;
+  if (s_begin < 0 || s_end < s_begin) throw std::invalid_argument("bad sample range");
+  const int tile_mod = st->tile_mod > 0 ? st->tile_mod : 1;
+  const int tile_rem = st->tile_mod > 0 ? st->tile_rem : 0;
+  if (tile_rem < 0 || tile_rem >= tile_mod) throw std::invalid_argument("tile_rem out of range");
+  uint32_t pool = st->pool_paths > 0 ? (uint32_t)st->pool_paths : (1u << 20);
+  pool = std::max(pool, 1024u);
+  ensure_workspace(s, pool);
+
+  RenderParams rp;
+  memcpy(&rp.cam, cam, sizeof(DCamera));
+  rp.width = st->width, rp.height = st->height;
+  rp.max_depth = st->max_depth;
+  rp.sample_begin = s_begin, rp.n_samples = s_end - s_begin;
+  rp.tiles_x = (st->width + 31) / 32;
+  const int tiles_y = (st->height + 31) / 32;
+  const int n_tiles = rp.tiles_x * tiles_y;
+  rp.n_my_tiles = tile_rem < n_tiles ? (n_tiles - tile_rem + tile_mod - 1) / tile_mod : 0;
+  rp.tile_mod = tile_mod, rp.tile_rem = tile_rem;
+  rp.pool = pool;
+  rp.seed = st->seed;
+
+  // valid pixels of this rank (for the paths statistic)
+  uint64_t my_pixels = 0;
+  for (int t = tile_rem; t < n_tiles; t += tile_mod) {
+    const int tx = t % rp.tiles_x, ty = t / rp.tiles_x;
+    const int w = std::min(32, st->width - tx * 32), h = std::min(32, st->height - ty * 32);
+    my_pixels += (uint64_t)w * h;
+  }
+
+  Ctl init;
+  memset(&init, 0, sizeof(init));
+  init.total_paths = rp.max_depth > 0 ? (unsigned long long)rp.n_my_tiles * 1024ull * (unsigned long long)rp.n_samples : 0ull;
+  CK(cudaMemcpyAsync(s->d_ctl.p, &init, sizeof(Ctl), cudaMemcpyHostToDevice, stream));
+
+  const bool counters = (st->flags & PTC_FLAG_COUNTERS) != 0;
+  const bool timing = (st->flags & PTC_FLAG_TIMING) != 0;
+  const Buffers b = buffers_of(s);
+  const int sms = s->sm_count;
+  const dim3 g_ext(sms * 8), g_shade(sms * 4), g_gen(sms * 4);
+
+  cudaEvent_t ev_begin, ev_end;
+  CK(cudaEventCreate(&ev_begin));
+  CK(cudaEventCreate(&ev_end));
+  size_t tev_used = 0;
+  auto tev = [&]() -> cudaEvent_t {
+    if (tev_used == s->timing_events.size()) {
+      cudaEvent_t e;
+      CK(cudaEventCreate(&e));
+      s->timing_events.push_back(e);
+    }
+    return s->timing_events[tev_used++];
+  };
+
+  CK(cudaEventRecord(ev_begin, stream));
+  int cur = 0;
+  k_advance<<<1, 32, 0, stream>>>(s->d_ctl.p, pool);
+  k_generate<<<g_gen, 256, 0, stream>>>(s->d_ctl.p, rp, b, cur);
+  uint64_t launches = 2;
+  std::deque<int> pending;
+  int ring_next = 0;
+  uint64_t it = 0;
+  const int check_every = 4;
+  bool finished = init.total_paths == 0;
+  while (!finished) {
+    if (timing) CK(cudaEventRecord(tev(), stream));
+    if (counters) k_extend<true><<<g_ext, 128, 0, stream>>>(s->d_ctl.p, s->ds, b, cur);
+    else k_extend<false><<<g_ext, 128, 0, stream>>>(s->d_ctl.p, s->ds, b, cur);
+    if (timing) CK(cudaEventRecord(tev(), stream));
+    k_shade<<<g_shade, 256, 0, stream>>>(s->d_ctl.p, s->ds, rp, b, cur, cur ^ 1, d_accum);
+    if (timing) CK(cudaEventRecord(tev(), stream));
+    k_advance<<<1, 32, 0, stream>>>(s->d_ctl.p, pool);
+    k_generate<<<g_gen, 256, 0, stream>>>(s->d_ctl.p, rp, b, cur ^ 1);
+    launches += 4;
+    cur ^= 1;
+    it++;
+    if (it % check_every == 0) {
+      // snapshot the control block; consume finished snapshots without stalling the launch queue.  The host only
+      // blocks when the ring is full, i.e. when it is kRing * check_every iterations ahead of what it has seen.
+      const int k = ring_next;
+      ring_next = (ring_next + 1) % ptc_scene::kRing;
+      CK(cudaMemcpyAsync(&s->h_ctl[k], s->d_ctl.p, sizeof(Ctl), cudaMemcpyDeviceToHost, stream));
+      CK(cudaEventRecord(s->ring_ev[k], stream));
+      pending.push_back(k);
+      while (!pending.empty()) {
+        const int o = pending.front();
+        const bool must_wait = (int)pending.size() >= ptc_scene::kRing;
+        if (!must_wait && cudaEventQuery(s->ring_ev[o]) == cudaErrorNotReady) {
+          cudaGetLastError();
+          break;
+        }
+        CK(cudaEventSynchronize(s->ring_ev[o]));
+        pending.pop_front();
+        if (s->h_ctl[o].done) {
+          finished = true;
+          break;
+        }
+      }
+    }
+  }
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(ev_end, stream));
+  Ctl fin;
+  CK(cudaMemcpyAsync(&s->h_ctl[0], s->d_ctl.p, sizeof(Ctl), cudaMemcpyDeviceToHost, stream));
+  CK(cudaStreamSynchronize(stream));
+  fin = s->h_ctl[0];
+  if (!fin.done) throw std::runtime_error("wavefront loop ended before all paths terminated");
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    stats->paths = rp.max_depth > 0 ? my_pixels * (uint64_t)rp.n_samples : 0;
+    stats->rays = fin.rays;
+    stats->iterations = fin.iterations;
+    stats->kernel_launches = launches;
+    float ms = 0.0f;
+    CK(cudaEventElapsedTime(&ms, ev_begin, ev_end));
+    stats->render_ms = ms;
+    if (timing) {
+      double ext = 0.0, shd = 0.0;
+      uint64_t n_ext = 0;
+      for (size_t k = 0; k + 3 <= tev_used; k += 3) {
+        float a = 0.0f, c = 0.0f;
+        CK(cudaEventElapsedTime(&a, s->timing_events[k], s->timing_events[k + 1]));
+        CK(cudaEventElapsedTime(&c, s->timing_events[k + 1], s->timing_events[k + 2]));
+        ext += a;
+        shd += c;
+        n_ext++;
+      }
+      stats->extend_ms = ext;
+      stats->shade_ms = shd;
+      stats->extend_launches = n_ext;
+    }
+    stats->nodes_visited = fin.nodes;
+    stats->tris_tested = fin.tris;
+    stats->mesh_rays = fin.mesh_rays;
+  }
+  cudaEventDestroy(ev_begin);
+  cudaEventDestroy(ev_end);
+}
+
+int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+
+#define PTC_GUARD_BEGIN try {
+#define PTC_GUARD_END                                   \
+  }                                                     \
+  catch (CudaError & e) { return fail(PTC_E_CUDA, e.what()); }             \
+  catch (std::bad_alloc & e) { return fail(PTC_E_NOMEM, e.what()); }       \
+  catch (std::logic_error & e) {                                           \
+    return fail(dynamic_cast<std::invalid_argument *>(&e) ? PTC_E_INVALID : PTC_E_STATE, e.what()); \
+  }                                                                        \
+  catch (std::exception & e) { return fail(PTC_E_INVALID, e.what()); }
+
+}  // namespace
+
+// =============================================================================================================
+extern "C" {
+
+const char *ptc_last_error(void) { return g_err.c_str(); }
+int ptc_abi_version(void) { return PTC_ABI_VERSION; }
+int ptc_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+ptc_scene *ptc_scene_create(void) {
+  try {
+    return new ptc_scene();
+  } catch (std::exception &e) {
+    g_err = e.what();
+    return nullptr;
+  }
+}
+void ptc_scene_destroy(ptc_scene *s) { delete s; }
+
+int ptc_scene_add_material(ptc_scene *s, const ptc_material *m) {
+  PTC_GUARD_BEGIN
+  if (!s || !m) throw std::invalid_argument("null argument");
+  if (s->committed) throw std::logic_error("scene already committed");
+  return s->hs.add_material(m);
+  PTC_GUARD_END
+}
+int ptc_scene_add_sphere(ptc_scene *s, const float c[3], float radius, int material) {
+  PTC_GUARD_BEGIN
+  if (!s || !c) throw std::invalid_argument("null argument");
+  if (s->committed) throw std::logic_error("scene already committed");
+  return s->hs.add_sphere(c, radius, material);
+  PTC_GUARD_END
+}
+int ptc_scene_add_plane(ptc_scene *s, const float p1[3], const float n[3], int material) {
+  PTC_GUARD_BEGIN
+  if (!s || !p1 || !n) throw std::invalid_argument("null argument");
+  if (s->committed) throw std::logic_error("scene already committed");
+  return s->hs.add_plane(p1, n, material);
+  PTC_GUARD_END
+}
+int ptc_scene_add_quad(ptc_scene *s, const float base[3], const float e0[3], const float e1[3], const float n[3], float d,
+                       float inv0, float inv1, int material) {
+  PTC_GUARD_BEGIN
+  if (!s || !base || !e0 || !e1 || !n) throw std::invalid_argument("null argument");
+  if (s->committed) throw std::logic_error("scene already committed");
+  return s->hs.add_quad(base, e0, e1, n, d, inv0, inv1, material);
+  PTC_GUARD_END
+}
+int ptc_scene_add_cube(ptc_scene *s, const float o2w[16], const float w2o[16], int material) {
+  PTC_GUARD_BEGIN
+  if (!s || !o2w || !w2o) throw std::invalid_argument("null argument");
+  if (s->committed) throw std::logic_error("scene already committed");
+  return s->hs.add_cube(o2w, w2o, material);
+  PTC_GUARD_END
+}
+int ptc_scene_add_mesh(ptc_scene *s, const float *tris, int64_t n, const float o2w[16], const float w2o[16], int material) {
+  PTC_GUARD_BEGIN
+  if (!s || !o2w || !w2o) throw std::invalid_argument("null argument");
+  if (s->committed) throw std::logic_error("scene already committed");
+  return s->hs.add_mesh(tris, n, o2w, w2o, material);
+  PTC_GUARD_END
+}
+int ptc_scene_set_sky_hdr(ptc_scene *s, const float *rgb, int32_t w, int32_t h) {
+  PTC_GUARD_BEGIN
+  if (!s) throw std::invalid_argument("null argument");
+  if (s->committed) throw std::logic_error("scene already committed");
+  s->hs.set_sky(rgb, w, h);
+  return 0;
+  PTC_GUARD_END
+}
+
+int ptc_scene_build(ptc_scene *s) {
+  PTC_GUARD_BEGIN
+  if (!s) throw std::invalid_argument("null argument");
+  s->hs.build_all();
+  return 0;
+  PTC_GUARD_END
+}
+
+int ptc_scene_commit(ptc_scene *s, int device) {
+  PTC_GUARD_BEGIN
+  if (!s) throw std::invalid_argument("null argument");
+  if (s->committed) throw std::logic_error("scene already committed");
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    throw CudaError("no CUDA device available (this library has no CPU fallback)");
+  }
+  if (device < 0 || device >= n) throw std::invalid_argument("device index out of range");
+  s->hs.build_all();  // host flattening: reference-BVH dead mask -> SAH -> 8-wide quantised BVH
+  CK(cudaSetDevice(device));
+  s->device = device;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  s->sm_count = prop.multiProcessorCount;
+  std::vector<DMesh> dm;
+  for (auto &m : s->hs.meshes) {
+    auto nodes = std::make_unique<DevBuf<float4>>();
+    auto tris = std::make_unique<DevBuf<float4>>();
+    auto nrm = std::make_unique<DevBuf<float4>>();
+    nodes->upload(reinterpret_cast<const float4 *>(m->nodes.data()), m->nodes.size() * 5);
+    tris->upload(reinterpret_cast<const float4 *>(m->tri48.data()), m->tri48.size() * 3);
+    nrm->upload(m->normals.data(), m->normals.size());
+    DMesh d;
+    d.nodes = nodes->p;
+    d.tris = tris->p;
+    d.normals = nrm->p;
+    d.n_nodes = (int32_t)m->nodes.size();
+    d.n_tris = (int32_t)m->tri48.size();
+    dm.push_back(d);
+    s->mesh_bufs.push_back(std::move(nodes));
+    s->mesh_bufs.push_back(std::move(tris));
+    s->mesh_bufs.push_back(std::move(nrm));
+  }
+  s->d_objects.upload(s->hs.objects.data(), s->hs.objects.size());
+  s->d_materials.upload(s->hs.materials.data(), s->hs.materials.size());
+  s->d_meshes.upload(dm.data(), dm.size());
+  if (!s->hs.sky.empty()) s->d_sky.upload(s->hs.sky.data(), s->hs.sky.size());
+  s->ds.objects = s->d_objects.p;
+  s->ds.materials = s->d_materials.p;
+  s->ds.meshes = s->d_meshes.p;
+  s->ds.sky = s->hs.sky.empty() ? nullptr : s->d_sky.p;
+  s->ds.n_objects = (int32_t)s->hs.objects.size();
+  s->ds.n_materials = (int32_t)s->hs.materials.size();
+  s->ds.n_meshes = (int32_t)dm.size();
+  s->ds.sky_w = s->hs.sky_w;
+  s->ds.sky_h = s->hs.sky_h;
+  CK(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
+  s->committed = true;
+  return 0;
+  PTC_GUARD_END
+}
+
+int ptc_scene_mesh_info(const ptc_scene *s, int object, ptc_mesh_info *info, uint8_t *dead, int32_t *order) {
+  PTC_GUARD_BEGIN
+  if (!s) throw std::invalid_argument("null argument");
+  if (object < 0 || (size_t)object >= s->hs.objects.size() || s->hs.objects[(size_t)object].type != OBJ_MESH)
+    throw std::invalid_argument("object is not a mesh");
+  const MeshBuild &m = *s->hs.meshes[(size_t)s->hs.objects[(size_t)object].mesh];
+  if (!m.built) throw std::logic_error("mesh not built yet (call ptc_scene_build or ptc_scene_commit first)");
+  if (info) {
+    info->triangles = m.n;
+    info->live_triangles = m.live;
+    info->ref_nodes = m.ref_nodes;
+    info->ref_leaves = m.ref_leaves;
+    info->ref_depth = m.ref_depth;
+    info->wide_nodes = (int64_t)m.nodes.size();
+    info->wide_depth = m.wide_depth;
+    info->node_bytes = (int64_t)m.nodes.size() * (int64_t)sizeof(Node8);
+    info->triangle_bytes = (int64_t)m.tri48.size() * (int64_t)sizeof(Tri48);
+  }
+  if (dead) memcpy(dead, m.dead.data(), (size_t)m.n);
+  if (order) memcpy(order, m.order.data(), (size_t)m.n * sizeof(int32_t));
+  return 0;
+  PTC_GUARD_END
+}
+
+int ptc_render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_settings *st, float *d_accum,
+                          void *cuda_stream, ptc_stats *stats) {
+  PTC_GUARD_BEGIN
+  require_committed(s);
+  render_accumulate(s, cam, st, d_accum, cuda_stream ? (cudaStream_t)cuda_stream : s->own_stream, stats);
+  return 0;
+  PTC_GUARD_END
+}
+
+int ptc_render(ptc_scene *s, const ptc_camera *cam, const ptc_render_settings *st, float *out_rgb, ptc_stats *stats) {
+  PTC_GUARD_BEGIN
+  require_committed(s);
+  if (!st || !out_rgb) throw std::invalid_argument("null argument");
+  if (st->width <= 0 || st->height <= 0 || st->spp <= 0) throw std::invalid_argument("bad render settings");
+  CK(cudaSetDevice(s->device));
+  const size_t n = (size_t)st->width * st->height * 3;
+  DevBuf<float> accum, out;
+  accum.alloc(n);
+  out.alloc(n);
+  cudaStream_t stream = s->own_stream;
+  CK(cudaMemsetAsync(accum.p, 0, n * sizeof(float), stream));
+  render_accumulate(s, cam, st, accum.p, stream, stats);
+  const float inv_spp = 1.0f / (float)st->spp;  // renderer.rs:85
+  k_scale<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(accum.p, out.p, n, inv_spp);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out_rgb, out.p, n * sizeof(float), cudaMemcpyDeviceToHost, stream));
+  CK(cudaStreamSynchronize(stream));
+  if (stats) stats->kernel_launches += 1;
+  return 0;
+  PTC_GUARD_END
+}
+
+int ptc_resolve_device(const float *d_rgb, int64_t n_pixels, float scale, uint32_t *d_out, void *cuda_stream) {
+  PTC_GUARD_BEGIN
+  if (!d_rgb || !d_out || n_pixels < 0) throw std::invalid_argument("bad argument");
+  if (n_pixels == 0) return 0;
+  k_resolve<<<(unsigned)((n_pixels + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(d_rgb, (size_t)n_pixels, scale, d_out);
+  CK(cudaGetLastError());
+  return 0;
+  PTC_GUARD_END
+}
+
+int ptc_resolve_u32(ptc_scene *s, const float *rgb, int64_t n_pixels, float scale, uint32_t *out) {
+  PTC_GUARD_BEGIN
+  require_committed(s);
+  if (!rgb || !out || n_pixels < 0) throw std::invalid_argument("bad argument");
+  if (n_pixels == 0) return 0;
+  CK(cudaSetDevice(s->device));
+  DevBuf<float> d_in;
+  DevBuf<uint32_t> d_out;
+  d_in.upload(rgb, (size_t)n_pixels * 3);
+  d_out.alloc((size_t)n_pixels);
+  k_resolve<<<(unsigned)((n_pixels + 255) / 256), 256, 0, s->own_stream>>>(d_in.p, (size_t)n_pixels, scale, d_out.p);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, d_out.p, (size_t)n_pixels * 4, cudaMemcpyDeviceToHost, s->own_stream));
+  CK(cudaStreamSynchronize(s->own_stream));
+  return 0;
+  PTC_GUARD_END
+}
+
+int ptc_intersect(ptc_scene *s, const float *origins, const float *dirs, int64_t n, float t_min, float t_max, ptc_hit *out,
+                  ptc_stats *stats) {
+  PTC_GUARD_BEGIN
+  require_committed(s);
+  if (n < 0 || (n > 0 && (!origins || !dirs || !out))) throw std::invalid_argument("bad argument");
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (n == 0) return 0;
+  CK(cudaSetDevice(s->device));
+  DevBuf<float> d_o, d_d;
+  DevBuf<ptc_hit> d_out;
+  DevBuf<unsigned long long> d_ctr;
+  d_o.upload(origins, (size_t)n * 3);
+  d_d.upload(dirs, (size_t)n * 3);
+  d_out.alloc((size_t)n);
+  d_ctr.alloc(3);
+  CK(cudaMemsetAsync(d_ctr.p, 0, 3 * sizeof(unsigned long long), s->own_stream));
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a));
+  CK(cudaEventCreate(&b));
+  CK(cudaEventRecord(a, s->own_stream));
+  k_intersect<<<(unsigned)((n + 127) / 128), 128, 0, s->own_stream>>>(s->ds, d_o.p, d_d.p, (size_t)n, t_min, t_max, d_out.p,
+                                                                      stats ? d_ctr.p : nullptr);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(b, s->own_stream));
+  CK(cudaMemcpyAsync(out, d_out.p, (size_t)n * sizeof(ptc_hit), cudaMemcpyDeviceToHost, s->own_stream));
+  unsigned long long ctr[3] = {0, 0, 0};
+  CK(cudaMemcpyAsync(ctr, d_ctr.p, sizeof(ctr), cudaMemcpyDeviceToHost, s->own_stream));
+  CK(cudaStreamSynchronize(s->own_stream));
+  if (stats) {
+    float ms = 0.0f;
+    CK(cudaEventElapsedTime(&ms, a, b));
+    stats->rays = (uint64_t)n;
+    stats->kernel_launches = 1;
+    stats->render_ms = ms;
+    stats->extend_ms = ms;
+    stats->extend_launches = 1;
+    stats->nodes_visited = ctr[0];
+    stats->tris_tested = ctr[1];
+    stats->mesh_rays = ctr[2];
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  return 0;
+  PTC_GUARD_END
+}
+
+int ptc_primary_rays(ptc_scene *s, const ptc_camera *cam, const ptc_render_settings *st, int32_t sample, float *out_o,
+                     float *out_d) {
+  PTC_GUARD_BEGIN
+  require_committed(s);
+  if (!cam || !st || !out_o || !out_d || st->width <= 0 || st->height <= 0) throw std::invalid_argument("bad argument");
+  CK(cudaSetDevice(s->device));
+  RenderParams rp;
+  memset(&rp, 0, sizeof(rp));
+  memcpy(&rp.cam, cam, sizeof(DCamera));
+  rp.width = st->width, rp.height = st->height, rp.seed = st->seed;
+  const size_t n = (size_t)st->width * st->height;
+  DevBuf<float> d_o, d_d;
+  d_o.alloc(n * 3);
+  d_d.alloc(n * 3);
+  k_primary_rays<<<(unsigned)((n + 255) / 256), 256, 0, s->own_stream>>>(rp, (uint32_t)sample, d_o.p, d_d.p);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out_o, d_o.p, n * 12, cudaMemcpyDeviceToHost, s->own_stream));
+  CK(cudaMemcpyAsync(out_d, d_d.p, n * 12, cudaMemcpyDeviceToHost, s->own_stream));
+  CK(cudaStreamSynchronize(s->own_stream));
+  return 0;
+  PTC_GUARD_END
+}
+
+int ptc_scatter(ptc_scene *s, int material, const float *ray_dirs, const float *positions, const float *normals,
+                const int32_t *front_face, const float *u4, int64_t n, int32_t *scattered, float *out_origin, float *out_dir,
+                float *attenuation, float *emitted) {
+  PTC_GUARD_BEGIN
+  require_committed(s);
+  if (material < 0 || (size_t)material >= s->hs.materials.size()) throw std::invalid_argument("material index out of range");
+  if (n < 0) throw std::invalid_argument("bad argument");
+  if (n == 0) return 0;
+  CK(cudaSetDevice(s->device));
+  const size_t N = (size_t)n;
+  DevBuf<float> d_dir, d_pos, d_nrm, d_u, d_oo, d_od, d_att, d_em;
+  DevBuf<int32_t> d_front, d_sc;
+  d_dir.upload(ray_dirs, N * 3);
+  d_pos.upload(positions, N * 3);
+  d_nrm.upload(normals, N * 3);
+  d_u.upload(u4, N * 4);
+  d_front.upload(front_face, N);
+  d_oo.alloc(N * 3), d_od.alloc(N * 3), d_att.alloc(N * 3), d_em.alloc(N * 3), d_sc.alloc(N);
+  k_scatter<<<(unsigned)((N + 127) / 128), 128, 0, s->own_stream>>>(s->hs.materials[(size_t)material], d_dir.p, d_pos.p, d_nrm.p,
+                                                                    d_front.p, d_u.p, N, d_sc.p, d_oo.p, d_od.p, d_att.p, d_em.p);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(scattered, d_sc.p, N * 4, cudaMemcpyDeviceToHost, s->own_stream));
+  CK(cudaMemcpyAsync(out_origin, d_oo.p, N * 12, cudaMemcpyDeviceToHost, s->own_stream));
+  CK(cudaMemcpyAsync(out_dir, d_od.p, N * 12, cudaMemcpyDeviceToHost, s->own_stream));
+  CK(cudaMemcpyAsync(attenuation, d_att.p, N * 12, cudaMemcpyDeviceToHost, s->own_stream));
+  CK(cudaMemcpyAsync(emitted, d_em.p, N * 12, cudaMemcpyDeviceToHost, s->own_stream));
+  CK(cudaStreamSynchronize(s->own_stream));
+  return 0;
+  PTC_GUARD_END
+}
+
+int ptc_philox(ptc_scene *s, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  PTC_GUARD_BEGIN
+  require_committed(s);
+  if (!ctr || !key || !out) throw std::invalid_argument("null argument");
+  CK(cudaSetDevice(s->device));
+  DevBuf<uint32_t> d;
+  d.alloc(4);
+  k_philox<<<1, 1, 0, s->own_stream>>>(U4{ctr[0], ctr[1], ctr[2], ctr[3]}, key[0], key[1], d.p);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, d.p, 16, cudaMemcpyDeviceToHost, s->own_stream));
+  CK(cudaStreamSynchronize(s->own_stream));
+  return 0;
+  PTC_GUARD_END
+}
+
+}  // extern "C"
