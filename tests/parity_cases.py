@@ -1,0 +1,270 @@
+"""Parity cases shared by the CPU run of the device headers (hostsim, `-m "not gpu"`) and the real thing (libptcore.so
+on a B200 through the C ABI, `-m gpu`).  Every case compares against the oracle on the same inputs.
+
+The bar (BASELINE.json north star): closest-hit primitive ids bit-exact except documented epsilon ties, t within 1e-5
+relative.  The code under test restates the reference's arithmetic without fusing, so the cases below actually demand
+more: ids exact with NO exceptions on these inputs, and t / position / normal bit-identical.
+"""
+import os
+
+import numpy as np
+
+from bindings import OracleScene, SimScene, compare_hits, oracle_get_ray, oracle_philox, oracle_resolve, oracle_scatter
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SCENES = os.path.join(ROOT, "scenes")
+
+
+class Backend:
+    """Uniform face over SimScene (g++ build of the device headers) and CoreScene (CUDA)."""
+
+    def __init__(self, kind, pt, scene):
+        self.kind, self.pt, self.scene = kind, pt, scene
+        if kind == "gpu":
+            self.impl = scene.to_core().commit(0)
+        else:
+            self.impl = SimScene(scene)
+
+    def intersect(self, o, d, t_min=1e-4, t_max=float("inf")):
+        if self.kind == "gpu":
+            return self.impl.intersect(o, d, t_min, t_max)
+        return self.impl.intersect(self.pt, o, d, t_min, t_max)
+
+    def mesh_info(self, obj):
+        return self.impl.mesh_info(obj) if self.kind == "gpu" else self.impl.mesh_info(self.pt, obj)
+
+    def __getattr__(self, name):
+        return getattr(self.impl, name)
+
+
+def rand_rays(rng, n, center, radius):
+    v = rng.normal(size=(n, 3))
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    o = np.asarray(center) + v * radius * rng.uniform(0.2, 3.0, size=(n, 1))
+    tgt = np.asarray(center) + rng.uniform(-1, 1, size=(n, 3)) * radius * 0.6
+    d = tgt - o
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    # what Ray::new would hold: f32, normalised in f32
+    d = d.astype(np.float32)
+    return o.astype(np.float32), d
+
+
+def composite_scene(pt):
+    """Every primitive type at once: scaled + rotated meshes (the t_world quirk of mesh_object.rs:312-314 is live when
+    scale != 1), a mesh with flat-node holes, sphere, cube, quad, plane."""
+    s = pt.Scene()
+    m0 = s.add_material(pt.lambertian((0.5, 0.5, 0.5)))
+    m1 = s.add_material(pt.dielectric(1.5))
+    s.add_obj(os.path.join(SCENES, "teapot", "teapot.obj"), m0, scale=(30, 30, 30), rotation=(10, 20, 30), position=(1, 2, 3))
+    s.add_sphere((20, 30, 10), 15.0, m1)
+    s.add_cube(m0, scale=(40, 5, 40), rotation=(0, 15, 0), position=(0, -10, 0))
+    s.add_obj(os.path.join(SCENES, "RayTracingText.obj"), m0, scale=(1, 1, 1), rotation=(-30, 45, 0), position=(-60, 0, 0))
+    s.add_quad(m0, scale=(50, 1, 50), rotation=(0, 0, 90), position=(60, 0, 0))
+    s.add_plane((0, -40, 0), (0, 1, 0.1), m0)
+    s.set_camera((0, 40, 150), (0, 10, 0), (0, 1, 0), 50.0, 4 / 3)
+    s.set_settings(64, 48, 4, 6)
+    return s
+
+
+def assert_hits_identical(pt, got, want):
+    r = compare_hits(got, want)
+    bad = r.pop("id_bad_idx")
+    assert r["id_mismatch"] == 0, (r, [(int(i), got[i], want[i]) for i in bad[:3]])
+    assert r["t_mismatch"] == 0, r
+    assert r["bit_exact_records"] == r["hits"], r  # t, position, normal, front_face all bit-identical
+    assert (got["material"] == want["material"]).all()
+    return r
+
+
+def check_primary_rays_shipped_scene(kind, pt, name, over):
+    s = pt.load_scene_from_json(os.path.join(SCENES, name))
+    st = s.render_settings(**over)
+    be = Backend(kind, pt, s)
+    o, d = be.primary_rays(s.camera, st, 0)
+    # the rays themselves: Philox jitter + Camera::get_ray against the oracle's camera
+    from bindings import oracle_philox as oph
+    for pix in (0, 17, st.width * st.height - 1):
+        x, y = pix % st.width, pix // st.width
+        r = oph([pix, 0, 0xffffffff, 0], [st.seed & 0xffffffff, st.seed >> 32])
+        ju, jv = np.float32(r[0] >> 8) * np.float32(2.0 ** -24), np.float32(r[1] >> 8) * np.float32(2.0 ** -24)
+        u = (np.float32(x) + ju) / np.float32(st.width)
+        v = (np.float32(y) + jv) / np.float32(st.height)
+        oo, od = oracle_get_ray(s.camera, float(u), float(v))
+        assert (o[pix] == oo).all() and (d[pix] == od).all()
+    got, stats = be.intersect(o, d)
+    want = OracleScene(s).intersect(pt, o, d)
+    r = assert_hits_identical(pt, got, want)
+    assert r["hits"] > 0.4 * len(o)
+    return r, stats
+
+
+def check_random_rays_composite(kind, pt, n=200000, seed=1):
+    s = composite_scene(pt)
+    be = Backend(kind, pt, s)
+    orc = OracleScene(s)
+    rng = np.random.default_rng(seed)
+    o, d = rand_rays(rng, n, (0, 20, 0), 60.0)
+    got, stats = be.intersect(o, d)
+    want = orc.intersect(pt, o, d)
+    r = assert_hits_identical(pt, got, want)
+    seen = set(np.unique(want["object"]).tolist())
+    assert seen >= {-1, 0, 1, 2, 3, 4, 5}, seen  # every primitive type was exercised, misses too
+    # bounded intervals: t_max cuts hits, the open/closed conventions of each primitive must agree
+    got2, _ = be.intersect(o[:50000], d[:50000], t_min=5.0, t_max=70.0)
+    want2 = orc.intersect(pt, o[:50000], d[:50000], t_min=5.0, t_max=70.0)
+    assert_hits_identical(pt, got2, want2)
+    return r, stats
+
+
+def check_mesh_build_facts(kind, pt):
+    s = pt.load_scene_from_json(os.path.join(SCENES, "semesterbild.json"))
+    be = Backend(kind, pt, s)
+    info, dead, order = be.mesh_info(3)
+    n, l, d, odead, oorder = OracleScene(s).mesh_bvh_info(3, info.triangles)
+    assert (info.ref_nodes, info.ref_leaves, info.ref_depth) == (n, l, d) == (3351, 1676, 11)  # KA2
+    assert (dead == odead).all() and (order == oorder).all()
+    assert info.live_triangles == 4748 - 1982 and info.triangle_bytes == 48 * info.live_triangles
+    assert info.node_bytes == 80 * info.wide_nodes
+
+
+def check_axis_aligned_and_degenerate_rays(kind, pt):
+    """Directions with exact zeros (1/0 = inf in every slab test), rays starting on surfaces, rays grazing box faces."""
+    s = composite_scene(pt)
+    be = Backend(kind, pt, s)
+    orc = OracleScene(s)
+    axes = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1], [0.6, 0.8, 0], [0, -0.6, 0.8]], np.float32)
+    rng = np.random.default_rng(5)
+    o = rng.uniform(-70, 70, size=(40000, 3)).astype(np.float32)
+    o[::7, 1] = np.float32(-7.5)   # on the cube's top face plane (y = -10 + 2.5)
+    o[::11] = np.round(o[::11])    # integer coordinates: exact ties with mesh vertices are plausible
+    d = axes[rng.integers(0, len(axes), size=len(o))]
+    got, _ = be.intersect(o, d)
+    want = orc.intersect(pt, o, d)
+    assert_hits_identical(pt, got, want)
+
+
+def check_scatter_all_materials(kind, pt, n=20000, tol_dir=1e-5, tol_att=1e-4):
+    """Material::scatter with explicit uniforms.  Deterministic branches must agree exactly; sampled directions may
+    differ by the ulp-level differences between CUDA's and glibc's sin/cos/log/atan."""
+    rng = np.random.default_rng(3)
+    nrm = rng.normal(size=(n, 3))
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    dirs = rng.normal(size=(n, 3))
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    flip = (dirs * nrm).sum(1) > 0
+    dirs[flip] *= -1
+    pos = rng.uniform(-50, 50, size=(n, 3))
+    ff = rng.integers(0, 2, size=n)
+    u4 = rng.uniform(0, 1, size=(n, 4)).astype(np.float32)
+    u4[:50, 0] = 0.0  # exercise u1.max(1e-6) of sample_ggx / sample_beckmann
+    mats = [pt.lambertian((0.7, 0.6, 0.5)), pt.checker((0.9, 0.9, 0.9), (0.1, 0.2, 0.3), 10.0), pt.metal((0.8, 0.8, 0.9), 0.3),
+            pt.metal((0.8, 0.8, 0.9), 0.0), pt.dielectric(1.52), pt.emissive((3, 2, 1)), pt.plastic((0.2, 0.5, 0.9), 1.5),
+            pt.rough_conductor((0.2, 0.3, 0.6), 0.1, "al", pt.DIST_GGX), pt.rough_conductor((1, 1, 1), 0.05, "cu", pt.DIST_BECKMANN),
+            pt.rough_conductor((1, 1, 1), 0.25, "au", pt.DIST_BECKMANN), pt.null_material()]
+    s = pt.Scene()
+    for m in mats:
+        s.add_material(m)
+    s.add_sphere((0, 0, 0), 1.0, 0)
+    be = Backend(kind, pt, s)
+    out = {}
+    for i, m in enumerate(s.materials):
+        g = be.scatter(i, dirs, pos, nrm, ff, u4)
+        w = oracle_scatter(m, dirs, pos, nrm, ff, u4)
+        assert (g[4] == w[4]).all()  # emitted
+        mism = g[0] != w[0]
+        # absorb / scatter decisions ride on `l.dot(n) <= 0`: allow a vanishing fraction of libm-induced flips
+        assert mism.mean() <= 2e-4, (i, int(mism.sum()))
+        both = (~mism) & (w[0] == 1)
+        if both.any():
+            assert np.abs(g[2][both] - w[2][both]).max() <= tol_dir, i
+            assert np.abs(g[1][both] - w[1][both]).max() <= 1e-5 * 50, i
+            rel = np.abs(g[3][both] - w[3][both]) / (np.abs(w[3][both]) + 1e-3)
+            assert rel.max() <= tol_att, (i, float(rel.max()))
+        out[i] = int(w[0].sum())
+    assert out[5] == 0 and out[10] == 0  # emissive and null never scatter
+    assert out[0] == n and out[4] == n
+    # checker parity on negative coordinates (Rust's % keeps the sign): both colours must appear and agree
+    g = be.scatter(1, dirs, pos, nrm, ff, u4)
+    w = oracle_scatter(s.materials[1], dirs, pos, nrm, ff, u4)
+    assert (g[3] == w[3]).all() and len(np.unique(w[3][:, 0])) == 2
+    return out
+
+
+def check_philox_and_resolve(kind, pt):
+    s = pt.Scene()
+    s.add_material(pt.lambertian((1, 1, 1)))
+    s.add_sphere((0, 0, 0), 1.0, 0)
+    be = Backend(kind, pt, s)
+    assert be.philox([0, 0, 0, 0], [0, 0]).tolist() == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert be.philox([0xffffffff] * 4, [0xffffffff] * 2).tolist() == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    c, k = [123, 456, 7, 0], [0xdeadbeef, 0x1234]
+    assert (be.philox(c, k) == oracle_philox(c, k)).all()
+    rng = np.random.default_rng(0)
+    img = rng.uniform(-0.2, 1.5, size=(5000, 3)).astype(np.float32)
+    img[0] = [np.nan, np.inf, -np.inf]
+    img[1] = [0.5, 0.5, 0.5]
+    got = be.resolve_u32(img)
+    assert (got == oracle_resolve(img)).all()
+    assert got[1] == 0x00B4B4B4  # KA1
+
+
+def check_sky_lookup(kind, pt):
+    """HDR equirect lookup (renderer.rs:40-54) is only reachable through a render; intersect must report misses."""
+    s = pt.Scene()
+    s.add_material(pt.lambertian((1, 1, 1)))
+    s.add_sphere((0, 0, -5), 1.0, 0)
+    be = Backend(kind, pt, s)
+    o = np.zeros((4, 3), np.float32)
+    d = np.array([[0, 0, -1], [0, 1, 0], [1, 0, 0], [0, 0, 1]], np.float32)
+    got, _ = be.intersect(o, d)
+    assert got["object"].tolist() == [0, -1, -1, -1] and got["triangle"].tolist() == [-1] * 4
+    assert got["t"][0] == 4.0 and got["front_face"][0] == 1
+
+
+def check_all_dead_mesh(kind, pt):
+    """A mesh that lies in one axis-aligned plane has a zero-extent root box: the reference can never hit it."""
+    s = pt.Scene()
+    m = s.add_material(pt.lambertian((1, 1, 1)))
+    v = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [2, 0, 0], [2, 1, 0]], np.float32)
+    idx = np.array([[0, 1, 2], [0, 2, 3], [1, 4, 5], [1, 5, 2], [0, 1, 5], [0, 4, 3]], np.int32)
+    s.add_mesh(v, idx, m)
+    be = Backend(kind, pt, s)
+    info, dead, _ = be.mesh_info(0)
+    assert info.live_triangles == 0 and dead.all()
+    o = np.array([[0.5, 0.5, 3.0]], np.float32)
+    d = np.array([[0, 0, -1.0]], np.float32)
+    got, _ = be.intersect(o, d)
+    want = OracleScene(s).intersect(pt, o, d)
+    assert got["object"][0] == -1 and want["object"][0] == -1
+
+
+def check_small_meshes(kind, pt):
+    """1-, 2- and 5-triangle meshes (root is a leaf; leaf of 4 + 1) and a large random soup."""
+    rng = np.random.default_rng(11)
+    for ntri in (1, 2, 5, 300):
+        s = pt.Scene()
+        m = s.add_material(pt.lambertian((1, 1, 1)))
+        v = rng.uniform(-1, 1, size=(ntri * 3, 3)).astype(np.float32)
+        idx = np.arange(ntri * 3, dtype=np.int32).reshape(-1, 3)
+        s.add_mesh(v, idx, m, scale=(2, 2, 2), rotation=(15, 25, 35), position=(0.5, 0, 0))
+        be = Backend(kind, pt, s)
+        o, d = rand_rays(rng, 20000, (0.5, 0, 0), 2.5)
+        got, _ = be.intersect(o, d)
+        want = OracleScene(s).intersect(pt, o, d)
+        r = assert_hits_identical(pt, got, want)
+        assert r["hits"] > 0
+
+
+def check_synthetic_heightfield(kind, pt, cells=64, n=100000):
+    s = pt.synthetic_scene(cells=cells)
+    be = Backend(kind, pt, s)
+    st = s.render_settings(width=256, height=144)
+    o, d = be.primary_rays(s.camera, st, 0)
+    got, stats = be.intersect(o, d)
+    want = OracleScene(s).intersect(pt, o, d)
+    r = assert_hits_identical(pt, got, want)
+    assert (want["object"] == 0).sum() > 0.3 * len(o)
+    rng = np.random.default_rng(2)
+    o2, d2 = rand_rays(rng, n, (0, 8, 0), 40.0)
+    assert_hits_identical(pt, be.intersect(o2, d2)[0], OracleScene(s).intersect(pt, o2, d2))
+    return r, stats
