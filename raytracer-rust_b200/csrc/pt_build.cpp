@@ -323,6 +323,12 @@ void collapse(const std::vector<B2> &b2, int32_t root, const int32_t *prim, cons
     }
 
     const QFrame fr = make_frame(n.box);
+    if (it.wide == 0)
+      for (int a = 0; a < 3; a++) {
+        m.root_lo[a] = fr.origin[a];
+        m.root_hi[a] = (float)((double)fr.origin[a] + 255.0 * fr.scale[a]);
+        if ((double)m.root_hi[a] < (double)fr.origin[a] + 255.0 * fr.scale[a]) m.root_hi[a] = std::nextafter(m.root_hi[a], INFINITY);
+      }
     uint8_t meta[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint8_t qlo[3][8], qhi[3][8];
     for (int a = 0; a < 3; a++)
@@ -450,6 +456,7 @@ void build_mesh(MeshBuild &m, int threads) {
     Tri48 z;
     z.t[0] = z.t[1] = z.t[2] = make_float4(0, 0, 0, 0);
     m.tri48.push_back(z);  // keep the buffer non-empty
+    for (int a = 0; a < 3; a++) m.root_lo[a] = 1.0f, m.root_hi[a] = -1.0f;
     m.built = true;
     return;
   }

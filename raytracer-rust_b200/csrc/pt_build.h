@@ -31,6 +31,7 @@ struct MeshBuild {
   std::vector<Tri48> tri48;
   std::vector<float4> normals;  // n
   int32_t wide_depth = 0;
+  float root_lo[3] = {1, 1, 1}, root_hi[3] = {-1, -1, -1};  // padded root frame (inverted = nothing to hit)
   bool built = false;
 };
 

@@ -120,31 +120,63 @@ PT_HD bool hit_cube(const float *f, const Ray &ray, float t_min, float t_max, Hi
   return true;
 }
 
-// src/mesh/mesh_object.rs:262-329
-template <bool COUNT>
-PT_HD bool hit_mesh(const float *f, const DMesh &mesh, const Ray &ray, float t_min, float t_max, Hit &h,
-                    TraversalCounters *ctr) {
+// Object-space ray of Mesh::hit (mesh_object.rs:264-287): d_raw = M^-1 (d,0); d = that, normalised at :287 and again by
+// Ray::new (ray.rs:15).
+struct MeshRay {
+  V3 o, d_raw, d;
+};
+PT_HD MeshRay mesh_object_ray(const float *w2o, const Ray &ray) {
+  MeshRay r;
+  r.o = mat_point(w2o, ray.o);
+  r.d_raw = mat_vector(w2o, ray.d);
+  r.d = normalized(normalized(r.d_raw));
+  return r;
+}
+// Conservative pre-test against the padded frame of the root node: false only if no live triangle can be hit in
+// (t_min, t_max).  Same NaN-dropping slab arithmetic as the node test in pt_bvh8.h.
+PT_HD bool mesh_root_may_hit(const DMesh &mesh, const MeshRay &r, float t_min, float t_max) {
+  const float idx = 1.0f / r.d.x, idy = 1.0f / r.d.y, idz = 1.0f / r.d.z;
+  const float ax = (mesh.root_lo[0] - r.o.x) * idx, bx = (mesh.root_hi[0] - r.o.x) * idx;
+  const float ay = (mesh.root_lo[1] - r.o.y) * idy, by = (mesh.root_hi[1] - r.o.y) * idy;
+  const float az = (mesh.root_lo[2] - r.o.z) * idz, bz = (mesh.root_hi[2] - r.o.z) * idz;
+  const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), t_min));
+  const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), t_max));
+  return tn <= tf;
+}
+
+// Second half of Mesh::hit (mesh_object.rs:293-326): object-space closest triangle -> world-space HitRecord, with the
+// closed-interval recheck on the (quirky) world t.
+PT_HD bool mesh_finish(const float *f, const DMesh &mesh, const Ray &ray, const MeshRay &mr, const MeshHit &mh, float t_min,
+                       float t_max, Hit &h) {
   const float *w2o = f, *o2w = f + 16;
-  const V3 o = mat_point(w2o, ray.o);
-  const V3 d_raw = mat_vector(w2o, ray.d);
-  const V3 d = normalized(normalized(d_raw));  // normalised at mesh_object.rs:287 and again by Ray::new (ray.rs:15)
-  if (COUNT) ctr->mesh_rays++;
-  MeshHit mh;
-  // the BVH is queried with the WORLD t bounds (mesh_object.rs:289-291)
-  if (!bvh8_closest<COUNT>(mesh, o, d, t_min, t_max, mh, ctr)) return false;
+  const V3 o = mr.o, d = mr.d;
   const V3 p_obj = o + d * mh.t;  // ray.at(t), bvh.rs:119
   const float4 nq = ldg4(mesh.normals + mh.tri);
   V3 n_obj = v3(nq.x, nq.y, nq.z);
   if (!(dot(d, n_obj) < 0.0f)) n_obj = -n_obj;  // bvh.rs:120-126
   const V3 pw = mat_point(o2w, p_obj);
   const V3 nw = normalized(mat_t_vector(w2o, n_obj));
-  const float t_world = mh.t * length(d_raw) / length(ray.d);  // mesh_object.rs:312-314
-  if (t_world < t_min || t_world > t_max) return false;          // closed (mesh_object.rs:316)
+  const float t_world = mh.t * length(mr.d_raw) / length(ray.d);  // mesh_object.rs:312-314
+  if (t_world < t_min || t_world > t_max) return false;             // closed (mesh_object.rs:316)
   h.t = t_world;
   h.triangle = (int32_t)mh.tri;
   set_pos(h, pw);
   set_face_normal(h, ray.d, nw);
   return true;
+}
+
+// src/mesh/mesh_object.rs:262-329, straight line (parity hooks and the hostsim harness; the renderer splits it into
+// root test / traversal / finish across kernels, ptcore.cu)
+template <bool COUNT>
+PT_HD bool hit_mesh(const float *f, const DMesh &mesh, const Ray &ray, float t_min, float t_max, Hit &h,
+                    TraversalCounters *ctr) {
+  const MeshRay mr = mesh_object_ray(f, ray);
+  if (!mesh_root_may_hit(mesh, mr, t_min, t_max)) return false;
+  if (COUNT) ctr->mesh_rays++;
+  MeshHit mh;
+  // the BVH is queried with the WORLD t bounds (mesh_object.rs:289-291)
+  if (!bvh8_closest<COUNT>(mesh, mr.o, mr.d, t_min, t_max, mh, ctr)) return false;
+  return mesh_finish(f, mesh, ray, mr, mh, t_min, t_max, h);
 }
 
 // HittableList::hit (hittable.rs:46-57): linear scan in insertion order with a shrinking t_max; each primitive's

@@ -13,6 +13,18 @@
 
 namespace pt {
 
+// The one place that fills a DMesh, so the CUDA upload and the hostsim harness cannot drift apart.
+inline DMesh make_dmesh(const MeshBuild &m, const float4 *nodes, const float4 *tris, const float4 *normals) {
+  DMesh d;
+  d.nodes = nodes;
+  d.tris = tris;
+  d.normals = normals;
+  d.n_nodes = (int32_t)m.nodes.size();
+  d.n_tris = (int32_t)m.tri48.size();
+  for (int a = 0; a < 3; a++) d.root_lo[a] = m.root_lo[a], d.root_hi[a] = m.root_hi[a];
+  return d;
+}
+
 struct HostScene {
   std::vector<DMaterial> materials;
   std::vector<DObject> objects;

@@ -67,6 +67,7 @@ struct DMesh {
   const float4 *tris;     // Tri48 array in leaf order
   const float4 *normals;  // Triangle.normal by original index (.w unused)
   int32_t n_nodes, n_tris;
+  float root_lo[3], root_hi[3];  // padded frame of the root node: a ray that misses it cannot hit any live triangle
 };
 
 struct DScene {

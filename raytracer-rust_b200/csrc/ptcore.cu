@@ -49,6 +49,8 @@ struct CudaError : std::runtime_error {
   } while (0)
 
 // ------------------------------------------------------------------------------------------------------------
+constexpr int kMaxRounds = 8;  // extend rounds = mesh objects a ray can be parked at; further meshes are walked in line
+
 // Device-side control block of one render (lives in device memory, mirrored to pinned host memory for polling)
 struct Ctl {
   unsigned long long next_path;   // next camera path index to start
@@ -62,6 +64,8 @@ struct Ctl {
   unsigned long long gen_first_path;
   uint32_t iterations;
   uint32_t done;
+  uint32_t tq_n[kMaxRounds + 1];   // parked-ray tasks per extend round (round r = r-th mesh a ray meets)
+  uint32_t tq_cursor[kMaxRounds];  // dynamic fetch cursor of the traversal warps, per round
 };
 
 struct RenderParams {
@@ -101,6 +105,8 @@ __global__ void k_advance(Ctl *ctl, uint32_t pool) {
   ctl->n_cur = n;  // generate appends the valid camera rays behind the survivors
   ctl->n_next = 0;
   ctl->work_extend = 0;
+  for (int r = 0; r < kMaxRounds; r++) ctl->tq_n[r] = 0u, ctl->tq_cursor[r] = 0u;
+  ctl->tq_n[kMaxRounds] = 0u;
   ctl->done = (g == 0 && n == 0) ? 1u : 0u;
 }
 
@@ -149,9 +155,110 @@ __global__ void __launch_bounds__(256) k_generate(Ctl *ctl, RenderParams rp, Buf
   }
 }
 
-// extend: persistent warps, 32 rays per fetch.
+// ------------------------------------------------------------------------------------------------------------
+// extend = HittableList::hit (hittable.rs:46-57) for every ray of the current buffer, as three kernels.
+//
+// The object list is scanned in insertion order exactly like the reference, but a thread never walks a BVH in line
+// with the analytic primitives.  Measured on the first version (one thread = one ray = the whole list, profiles/r1_v1_*):
+// the traversal code ran with 7.5 of 32 lanes active and the triangle test with 2, because most rays miss a mesh's
+// root box and the rest need wildly different numbers of steps.  So:
+//
+//   k_extend_pre   every ray, full warps: analytic primitives up to the first mesh whose (conservative) root-frame test
+//                  passes; such a ray is PARKED: its partial closest hit goes to the hit record it owns, and a task
+//                  {ray, object index, object-space ray, closest_so_far} is appended to a queue (one atomic per warp)
+//   k_traverse     persistent warps over the task queue: each lane walks its own BVH one step at a time (one node or
+//                  one triangle per turn) and a lane that finishes fetches the next task at once, so warps stay
+//                  populated however uneven the rays are
+//   k_extend_post  every task, full warps: second half of Mesh::hit (world-space record, closed-interval recheck), then
+//                  the scan resumes at the next object; a ray that meets another mesh is parked again (next round)
+//
+// Every object still sees exactly the `closest_so_far` it would have seen in the reference's sequential scan, so the
+// tie-breaking and interval conventions of hittable.rs:50-55 are untouched.
+constexpr int kExtendThreads = 128;
+constexpr uint32_t kRefillLanes = 8;  // a traversal warp fetches new tasks once this many lanes are idle
+
+struct ExtendOut {
+  Buffers b;
+  int2 *ids;  // (object, triangle) per ray, only for ptc_intersect (nullptr in renders)
+};
+
+struct TaskQ {       // [round & 1]
+  uint2 *ray[2];     // x = ray index, y = object index of the mesh
+  float4 *o[2];      // object-space origin, closest_so_far (the t_max Mesh::hit was called with)
+  float4 *d[2];      // object-space direction (normalised twice, mesh_object.rs:287 + ray.rs:15)
+  float2 *res[2];    // traversal result: t (object space), original triangle index or 0xffffffff
+};
+
+__device__ __forceinline__ void write_hit(const ExtendOut &out, uint32_t i, const Hit &h) {
+  out.b.hit0[i] = make_float4(h.px, h.py, h.pz, h.t);
+  out.b.hit1[i] = make_float4(h.nx, h.ny, h.nz, u2f(kHitBit | (h.front_face ? kFrontBit : 0u) | ((uint32_t)h.material & kMatMask)));
+  if (out.ids) out.ids[i] = make_int2(h.object, h.triangle);
+}
+__device__ __forceinline__ void write_miss(const ExtendOut &out, uint32_t i) {
+  out.b.hit1[i] = make_float4(0.0f, 0.0f, 0.0f, u2f(0u));
+  if (out.ids) out.ids[i] = make_int2(-1, -1);
+}
+
+// Scan objects [k_begin, n).  Returns the index of the mesh the ray has to be parked at (its object-space ray in
+// `park_ray`), or -1 when the scan is complete.  allow_park == false walks meshes in line (only used when a scene
+// has more mesh objects than kMaxRounds).
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_extend(Ctl *ctl, DScene sc, Buffers b, int src) {
+__device__ __forceinline__ int scan_objects(const DScene &sc, const Ray &ray, float t_min, float &closest, Hit &best,
+                                            bool &improved, int k_begin, bool allow_park, MeshRay &park_ray,
+                                            TraversalCounters *tc) {
+  for (int k = k_begin; k < sc.n_objects; k++) {
+    const DObject *ob = sc.objects + k;
+    const int type = ob->type;
+    Hit tmp;
+    tmp.triangle = -1;
+    bool hit;
+    if (type == OBJ_MESH) {
+      const DMesh &mesh = sc.meshes[ob->mesh];
+      const MeshRay mr = mesh_object_ray(ob->f, ray);
+      if (!mesh_root_may_hit(mesh, mr, t_min, closest)) continue;  // cannot hit: same as Mesh::hit returning None
+      if (allow_park) {
+        park_ray = mr;
+        return k;
+      }
+      if (COUNT) tc->mesh_rays++;
+      MeshHit mh;
+      hit = bvh8_closest<COUNT>(mesh, mr.o, mr.d, t_min, closest, mh, tc) && mesh_finish(ob->f, mesh, ray, mr, mh, t_min, closest, tmp);
+    } else if (type == OBJ_SPHERE) hit = hit_sphere(ob->f, ray, t_min, closest, tmp);
+    else if (type == OBJ_QUAD) hit = hit_quad(ob->f, ray, t_min, closest, tmp);
+    else if (type == OBJ_CUBE) hit = hit_cube(ob->f, ray, t_min, closest, tmp);
+    else hit = hit_plane(ob->f, ray, t_min, closest, tmp);
+    if (hit) {
+      improved = true;
+      closest = tmp.t;
+      best = tmp;
+      best.object = k;
+      best.material = ob->material;
+    }
+  }
+  return -1;
+}
+
+// warp-aggregated append of the parked lanes to the task queue of round `round`
+__device__ __forceinline__ void park_tasks(Ctl *ctl, const TaskQ &tq, int round, int park, uint32_t i, const MeshRay &mr,
+                                           float closest) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t mask = __ballot_sync(0xffffffffu, park >= 0);
+  if (mask == 0u) return;
+  uint32_t slot0 = 0;
+  if (lane == 0) slot0 = atomicAdd(&ctl->tq_n[round], (uint32_t)__popc(mask));
+  slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+  if (park >= 0) {
+    const uint32_t slot = slot0 + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+    const int par = round & 1;
+    tq.ray[par][slot] = make_uint2(i, (uint32_t)park);
+    tq.o[par][slot] = make_float4(mr.o.x, mr.o.y, mr.o.z, closest);
+    tq.d[par][slot] = make_float4(mr.d.x, mr.d.y, mr.d.z, 0.0f);
+  }
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kExtendThreads) k_extend_pre(Ctl *ctl, DScene sc, ExtendOut out, TaskQ tq, int src, float t_min,
+                                                               float t_max, int allow_park) {
   const uint32_t n = ctl->n_cur;
   const uint32_t lane = threadIdx.x & 31u;
   TraversalCounters tc{0u, 0u, 0u};
@@ -161,19 +268,136 @@ __global__ void __launch_bounds__(128) k_extend(Ctl *ctl, DScene sc, Buffers b, 
     base = __shfl_sync(0xffffffffu, base, 0);
     if (base >= n) break;
     const uint32_t i = base + lane;
+    int park = -1;
+    MeshRay mr;
+    float closest = t_max;
     if (i < n) {
-      const float4 o4 = b.ray_o[src][i], d4 = b.ray_d[src][i];
+      const float4 o4 = out.b.ray_o[src][i], d4 = out.b.ray_d[src][i];
       const Ray ray{v3(o4.x, o4.y, o4.z), v3(d4.x, d4.y, d4.z)};
-      Hit h;
-      const bool hit = scene_hit<COUNT>(sc, ray, kEps, INFINITY, h, &tc);  // renderer.rs:24
-      if (hit) {
-        b.hit0[i] = make_float4(h.px, h.py, h.pz, h.t);
-        b.hit1[i] = make_float4(h.nx, h.ny, h.nz, u2f(kHitBit | (h.front_face ? kFrontBit : 0u) | ((uint32_t)h.material & kMatMask)));
-      } else {
-        b.hit1[i] = make_float4(0.0f, 0.0f, 0.0f, u2f(0u));
-      }
+      Hit best;
+      bool improved = false;
+      park = scan_objects<COUNT>(sc, ray, t_min, closest, best, improved, 0, allow_park != 0, mr, &tc);  // renderer.rs:24
+      if (improved) write_hit(out, i, best);
+      else write_miss(out, i);
     }
-    __syncwarp();
+    park_tasks(ctl, tq, 0, park, i, mr, closest);
+  }
+  if (COUNT) {
+    atomicAdd(&ctl->nodes, (unsigned long long)tc.nodes);
+    atomicAdd(&ctl->tris, (unsigned long long)tc.tris);
+    atomicAdd(&ctl->mesh_rays, (unsigned long long)tc.mesh_rays);
+  }
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kExtendThreads) k_traverse(Ctl *ctl, DScene sc, TaskQ tq, int round, float t_min) {
+  const uint32_t n = ctl->tq_n[round];
+  const int par = round & 1;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  TraversalCounters tc{0u, 0u, 0u};
+  TravState s;
+  DMesh mesh;  // the two pointers of the mesh this lane walks, kept in registers
+  mesh.nodes = nullptr, mesh.tris = nullptr;
+  uint2 stack[kTraversalStack];
+  int sp = 0;
+  bool active = false;
+  uint32_t task = 0;
+  bool exhausted = n == 0u;
+  for (;;) {
+    const uint32_t idle = __ballot_sync(0xffffffffu, !active);
+    if (!exhausted && (idle == 0xffffffffu || (uint32_t)__popc(idle) >= kRefillLanes)) {
+      const uint32_t cnt = (uint32_t)__popc(idle);
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(&ctl->tq_cursor[round], cnt);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (!active) {
+        const uint32_t j = base + (uint32_t)__popc(idle & lt_mask);
+        if (j < n) {
+          const uint2 rk = tq.ray[par][j];
+          const float4 o4 = tq.o[par][j], d4 = tq.d[par][j];
+          const DMesh *gm = sc.meshes + sc.objects[rk.y].mesh;
+          mesh.nodes = gm->nodes;
+          mesh.tris = gm->tris;
+          trav_begin(s, v3(o4.x, o4.y, o4.z), v3(d4.x, d4.y, d4.z), t_min, o4.w);  // world t bounds, mesh_object.rs:289-291
+          sp = 0;
+          task = j;
+          active = true;
+          if (COUNT) tc.mesh_rays++;
+        }
+      }
+      if (base + cnt >= n) exhausted = true;
+    }
+    if (__ballot_sync(0xffffffffu, active) == 0u) {
+      if (exhausted) break;
+      continue;
+    }
+    if (active) {
+      if (!trav_has_tri(s) && !trav_has_node(s)) {
+        if (sp > 0) {
+          s.ng = stack[--sp];
+        } else {
+          tq.res[par][task] = make_float2(s.best_t, u2f(s.best_tri));
+          active = false;
+        }
+      }
+      if (active && !trav_has_tri(s) && trav_has_node(s)) trav_node<COUNT>(mesh, s, stack, sp, &tc);
+      if (active && trav_has_tri(s)) trav_tri<COUNT>(mesh, s, &tc);
+    }
+  }
+  if (COUNT) {
+    atomicAdd(&ctl->nodes, (unsigned long long)tc.nodes);
+    atomicAdd(&ctl->tris, (unsigned long long)tc.tris);
+    atomicAdd(&ctl->mesh_rays, (unsigned long long)tc.mesh_rays);
+  }
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kExtendThreads) k_extend_post(Ctl *ctl, DScene sc, ExtendOut out, TaskQ tq, int src, int round,
+                                                                float t_min, float t_max, int allow_park) {
+  const uint32_t n = ctl->tq_n[round];
+  const int par = round & 1;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  TraversalCounters tc{0u, 0u, 0u};
+  for (uint32_t base = warp_id * 32u; base < n; base += warps_total * 32u) {
+    const uint32_t j = base + lane;
+    int park = -1;
+    MeshRay mr;
+    float closest = t_max;
+    uint32_t i = 0;
+    if (j < n) {
+      const uint2 rk = tq.ray[par][j];
+      const float2 res = tq.res[par][j];
+      i = rk.x;
+      const int k = (int)rk.y;
+      const float4 o4 = out.b.ray_o[src][i], d4 = out.b.ray_d[src][i];
+      const Ray ray{v3(o4.x, o4.y, o4.z), v3(d4.x, d4.y, d4.z)};
+      const bool any = (f2u(out.b.hit1[i].w) & kHitBit) != 0u;
+      if (any) closest = out.b.hit0[i].w;  // == the t_max the traversal ran with
+      Hit best;
+      best.triangle = -1;
+      bool improved = false;
+      const uint32_t tri = f2u(res.y);
+      if (tri != 0xffffffffu) {
+        const DObject *ob = sc.objects + k;
+        const MeshRay omr = mesh_object_ray(ob->f, ray);  // same inputs, same bits as in k_extend_pre
+        MeshHit mh;
+        mh.t = res.x, mh.tri = tri, mh.order = 0u;
+        Hit tmp;
+        if (mesh_finish(ob->f, sc.meshes[ob->mesh], ray, omr, mh, t_min, closest, tmp)) {
+          improved = true;
+          closest = tmp.t;
+          best = tmp;
+          best.object = k;
+          best.material = ob->material;
+        }
+      }
+      park = scan_objects<COUNT>(sc, ray, t_min, closest, best, improved, k + 1, allow_park != 0, mr, &tc);
+      if (improved) write_hit(out, i, best);  // otherwise the record parked by the previous stage stands
+    }
+    park_tasks(ctl, tq, round + 1, park, i, mr, closest);
   }
   if (COUNT) {
     atomicAdd(&ctl->nodes, (unsigned long long)tc.nodes);
@@ -260,33 +484,33 @@ __global__ void k_resolve(const float *rgb, size_t n_pixels, float scale, uint32
 }
 
 // ---- parity hooks: the same device functions, driven by caller-provided inputs ------------------------------
-__global__ void k_intersect(DScene sc, const float *o, const float *d, size_t n, float t_min, float t_max, ptc_hit *out,
-                            unsigned long long *counters) {
+// ptc_intersect runs the very kernel the renderer uses (k_extend); these two only repack its inputs / outputs.
+__global__ void k_pack_rays(const float *o, const float *d, size_t n, float4 *ro, float4 *rd) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  TraversalCounters tc{0u, 0u, 0u};
-  if (i < n) {
-    const Ray ray{v3(o[i * 3], o[i * 3 + 1], o[i * 3 + 2]), v3(d[i * 3], d[i * 3 + 1], d[i * 3 + 2])};
-    Hit h;
-    ptc_hit r;
-    memset(&r, 0, sizeof(r));
-    if (scene_hit<true>(sc, ray, t_min, t_max, h, &tc)) {
-      r.object = h.object;
-      r.triangle = h.triangle;
-      r.t = h.t;
-      r.position[0] = h.px, r.position[1] = h.py, r.position[2] = h.pz;
-      r.normal[0] = h.nx, r.normal[1] = h.ny, r.normal[2] = h.nz;
-      r.front_face = h.front_face;
-      r.material = h.material;
-    } else {
-      r.object = -1, r.triangle = -1, r.material = -1;
-    }
-    out[i] = r;
+  if (i >= n) return;
+  ro[i] = make_float4(o[i * 3], o[i * 3 + 1], o[i * 3 + 2], 0.0f);
+  rd[i] = make_float4(d[i * 3], d[i * 3 + 1], d[i * 3 + 2], 0.0f);
+}
+__global__ void k_unpack_hits(const float4 *hit0, const float4 *hit1, const int2 *ids, size_t n, ptc_hit *out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  ptc_hit r;
+  memset(&r, 0, sizeof(r));
+  const float4 h1 = hit1[i];
+  const uint32_t bits = f2u(h1.w);
+  if (bits & kHitBit) {
+    const float4 h0 = hit0[i];
+    const int2 id = ids[i];
+    r.object = id.x, r.triangle = id.y;
+    r.t = h0.w;
+    r.position[0] = h0.x, r.position[1] = h0.y, r.position[2] = h0.z;
+    r.normal[0] = h1.x, r.normal[1] = h1.y, r.normal[2] = h1.z;
+    r.front_face = (bits & kFrontBit) ? 1 : 0;
+    r.material = (int32_t)(bits & kMatMask);
+  } else {
+    r.object = -1, r.triangle = -1, r.material = -1;
   }
-  if (counters) {
-    atomicAdd(counters + 0, (unsigned long long)tc.nodes);
-    atomicAdd(counters + 1, (unsigned long long)tc.tris);
-    atomicAdd(counters + 2, (unsigned long long)tc.mesh_rays);
-  }
+  out[i] = r;
 }
 
 __global__ void k_primary_rays(RenderParams rp, uint32_t sample, float *out_o, float *out_d) {
@@ -367,6 +591,10 @@ struct ptc_scene {
   // render workspace
   uint32_t pool = 0;
   DevBuf<float4> w_ray_o[2], w_ray_d[2], w_beta[2], w_hit0, w_hit1;
+  DevBuf<uint2> w_tq_ray[2];
+  DevBuf<float4> w_tq_o[2], w_tq_d[2];
+  DevBuf<float2> w_tq_res[2];
+  int mesh_objects = 0;  // mesh entries in object_list = extend rounds needed
   DevBuf<Ctl> d_ctl;
   Ctl *h_ctl = nullptr;  // pinned ring
   static constexpr int kRing = 4;
@@ -386,6 +614,30 @@ struct ptc_scene {
 
 namespace {
 
+// One extend pass = pre, then (traverse, post) once per mesh object a ray can meet.  Returns the number of launches.
+int launch_extend(cudaStream_t stream, int sm_count, int mesh_objects, Ctl *ctl, const DScene &ds, const ExtendOut &eo,
+                  const TaskQ &tq, int src, float t_min, float t_max, bool counters) {
+  const int rounds = mesh_objects < kMaxRounds ? mesh_objects : kMaxRounds;
+  const dim3 grid(sm_count * 8);
+  int launches = 1;
+  if (counters) k_extend_pre<true><<<grid, kExtendThreads, 0, stream>>>(ctl, ds, eo, tq, src, t_min, t_max, rounds > 0);
+  else k_extend_pre<false><<<grid, kExtendThreads, 0, stream>>>(ctl, ds, eo, tq, src, t_min, t_max, rounds > 0);
+  for (int r = 0; r < rounds; r++) {
+    const int park_more = (r + 1 < rounds) ? 1 : 0;  // after the last round the remaining meshes (if any) are walked in line
+    if (counters) {
+      k_traverse<true><<<grid, kExtendThreads, 0, stream>>>(ctl, ds, tq, r, t_min);
+      k_extend_post<true><<<grid, kExtendThreads, 0, stream>>>(ctl, ds, eo, tq, src, r, t_min, t_max, park_more);
+    } else {
+      k_traverse<false><<<grid, kExtendThreads, 0, stream>>>(ctl, ds, tq, r, t_min);
+      k_extend_post<false><<<grid, kExtendThreads, 0, stream>>>(ctl, ds, eo, tq, src, r, t_min, t_max, park_more);
+    }
+    launches += 2;
+  }
+  return launches;
+}
+
+TaskQ taskq_of(ptc_scene *s);
+
 void ensure_workspace(ptc_scene *s, uint32_t pool) {
   if (s->pool == pool && s->h_ctl) return;
   for (int k = 0; k < 2; k++) {
@@ -395,6 +647,13 @@ void ensure_workspace(ptc_scene *s, uint32_t pool) {
   }
   s->w_hit0.alloc(pool);
   s->w_hit1.alloc(pool);
+  if (s->mesh_objects > 0)
+    for (int k = 0; k < 2; k++) {
+      s->w_tq_ray[k].alloc(pool);
+      s->w_tq_o[k].alloc(pool);
+      s->w_tq_d[k].alloc(pool);
+      s->w_tq_res[k].alloc(pool);
+    }
   s->d_ctl.alloc(1);
   if (!s->h_ctl) {
     CK(cudaMallocHost(&s->h_ctl, sizeof(Ctl) * ptc_scene::kRing));
@@ -413,6 +672,17 @@ Buffers buffers_of(ptc_scene *s) {
   b.hit0 = s->w_hit0.p;
   b.hit1 = s->w_hit1.p;
   return b;
+}
+
+TaskQ taskq_of(ptc_scene *s) {
+  TaskQ q;
+  for (int k = 0; k < 2; k++) {
+    q.ray[k] = s->w_tq_ray[k].p;
+    q.o[k] = s->w_tq_o[k].p;
+    q.d[k] = s->w_tq_d[k].p;
+    q.res[k] = s->w_tq_res[k].p;
+  }
+  return q;
 }
 
 void require_committed(const ptc_scene *s) {
@@ -467,8 +737,9 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
   const bool counters = (st->flags & PTC_FLAG_COUNTERS) != 0;
   const bool timing = (st->flags & PTC_FLAG_TIMING) != 0;
   const Buffers b = buffers_of(s);
+  const TaskQ tq = taskq_of(s);
   const int sms = s->sm_count;
-  const dim3 g_ext(sms * 8), g_shade(sms * 4), g_gen(sms * 4);
+  const dim3 g_shade(sms * 4), g_gen(sms * 4);
 
   cudaEvent_t ev_begin, ev_end;
   CK(cudaEventCreate(&ev_begin));
@@ -495,8 +766,8 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
   bool finished = init.total_paths == 0;
   while (!finished) {
     if (timing) CK(cudaEventRecord(tev(), stream));
-    if (counters) k_extend<true><<<g_ext, 128, 0, stream>>>(s->d_ctl.p, s->ds, b, cur);
-    else k_extend<false><<<g_ext, 128, 0, stream>>>(s->d_ctl.p, s->ds, b, cur);
+    const ExtendOut eo{b, nullptr};
+    launches += launch_extend(stream, sms, s->mesh_objects, s->d_ctl.p, s->ds, eo, tq, cur, kEps, INFINITY, counters) - 1;
     if (timing) CK(cudaEventRecord(tev(), stream));
     k_shade<<<g_shade, 256, 0, stream>>>(s->d_ctl.p, s->ds, rp, b, cur, cur ^ 1, d_accum);
     if (timing) CK(cudaEventRecord(tev(), stream));
@@ -693,12 +964,7 @@ int ptc_scene_commit(ptc_scene *s, int device) {
     nodes->upload(reinterpret_cast<const float4 *>(m->nodes.data()), m->nodes.size() * 5);
     tris->upload(reinterpret_cast<const float4 *>(m->tri48.data()), m->tri48.size() * 3);
     nrm->upload(m->normals.data(), m->normals.size());
-    DMesh d;
-    d.nodes = nodes->p;
-    d.tris = tris->p;
-    d.normals = nrm->p;
-    d.n_nodes = (int32_t)m->nodes.size();
-    d.n_tris = (int32_t)m->tri48.size();
+    const DMesh d = make_dmesh(*m, nodes->p, tris->p, nrm->p);
     dm.push_back(d);
     s->mesh_bufs.push_back(std::move(nodes));
     s->mesh_bufs.push_back(std::move(tris));
@@ -717,6 +983,9 @@ int ptc_scene_commit(ptc_scene *s, int device) {
   s->ds.n_meshes = (int32_t)dm.size();
   s->ds.sky_w = s->hs.sky_w;
   s->ds.sky_h = s->hs.sky_h;
+  s->mesh_objects = 0;
+  for (const DObject &o : s->hs.objects)
+    if (o.type == OBJ_MESH) s->mesh_objects++;
   CK(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
   s->committed = true;
   return 0;
@@ -815,31 +1084,57 @@ int ptc_intersect(ptc_scene *s, const float *origins, const float *dirs, int64_t
   if (stats) memset(stats, 0, sizeof(*stats));
   if (n == 0) return 0;
   CK(cudaSetDevice(s->device));
+  if (n > (int64_t)0x7fffffff) throw std::invalid_argument("too many rays for one call");
   DevBuf<float> d_o, d_d;
   DevBuf<ptc_hit> d_out;
-  DevBuf<unsigned long long> d_ctr;
+  DevBuf<float4> ro, rd, h0, h1;
+  DevBuf<int2> ids;
+  DevBuf<Ctl> ctl;
   d_o.upload(origins, (size_t)n * 3);
   d_d.upload(dirs, (size_t)n * 3);
   d_out.alloc((size_t)n);
-  d_ctr.alloc(3);
-  CK(cudaMemsetAsync(d_ctr.p, 0, 3 * sizeof(unsigned long long), s->own_stream));
+  ro.alloc((size_t)n), rd.alloc((size_t)n), h0.alloc((size_t)n), h1.alloc((size_t)n), ids.alloc((size_t)n);
+  Ctl init;
+  memset(&init, 0, sizeof(init));
+  init.n_cur = (uint32_t)n;
+  ctl.upload(&init, 1);
+  cudaStream_t st = s->own_stream;
+  const unsigned nb = (unsigned)((n + 255) / 256);
+  k_pack_rays<<<nb, 256, 0, st>>>(d_o.p, d_d.p, (size_t)n, ro.p, rd.p);
+  ExtendOut eo;
+  eo.b.ray_o[0] = eo.b.ray_o[1] = ro.p;
+  eo.b.ray_d[0] = eo.b.ray_d[1] = rd.p;
+  eo.b.beta[0] = eo.b.beta[1] = nullptr;
+  eo.b.hit0 = h0.p, eo.b.hit1 = h1.p;
+  eo.ids = ids.p;
   cudaEvent_t a, b;
   CK(cudaEventCreate(&a));
   CK(cudaEventCreate(&b));
-  CK(cudaEventRecord(a, s->own_stream));
-  k_intersect<<<(unsigned)((n + 127) / 128), 128, 0, s->own_stream>>>(s->ds, d_o.p, d_d.p, (size_t)n, t_min, t_max, d_out.p,
-                                                                      stats ? d_ctr.p : nullptr);
+  CK(cudaEventRecord(a, st));
+  DevBuf<uint2> q_ray[2];
+  DevBuf<float4> q_o[2], q_d[2];
+  DevBuf<float2> q_res[2];
+  TaskQ tq;
+  for (int k = 0; k < 2; k++) {
+    const size_t cap = s->mesh_objects > 0 ? (size_t)n : 1;
+    q_ray[k].alloc(cap), q_o[k].alloc(cap), q_d[k].alloc(cap), q_res[k].alloc(cap);
+    tq.ray[k] = q_ray[k].p, tq.o[k] = q_o[k].p, tq.d[k] = q_d[k].p, tq.res[k] = q_res[k].p;
+  }
+  const int ext_launches = launch_extend(st, s->sm_count, s->mesh_objects, ctl.p, s->ds, eo, tq, 0, t_min, t_max, true);
   CK(cudaGetLastError());
-  CK(cudaEventRecord(b, s->own_stream));
+  CK(cudaEventRecord(b, st));
+  k_unpack_hits<<<nb, 256, 0, st>>>(h0.p, h1.p, ids.p, (size_t)n, d_out.p);
+  CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, d_out.p, (size_t)n * sizeof(ptc_hit), cudaMemcpyDeviceToHost, s->own_stream));
-  unsigned long long ctr[3] = {0, 0, 0};
-  CK(cudaMemcpyAsync(ctr, d_ctr.p, sizeof(ctr), cudaMemcpyDeviceToHost, s->own_stream));
+  Ctl fin;
+  CK(cudaMemcpyAsync(&fin, ctl.p, sizeof(Ctl), cudaMemcpyDeviceToHost, s->own_stream));
   CK(cudaStreamSynchronize(s->own_stream));
+  const unsigned long long ctr[3] = {fin.nodes, fin.tris, fin.mesh_rays};
   if (stats) {
     float ms = 0.0f;
     CK(cudaEventElapsedTime(&ms, a, b));
     stats->rays = (uint64_t)n;
-    stats->kernel_launches = 1;
+    stats->kernel_launches = 2 + (uint64_t)ext_launches;
     stats->render_ms = ms;
     stats->extend_ms = ms;
     stats->extend_launches = 1;

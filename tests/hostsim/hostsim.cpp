@@ -67,12 +67,8 @@ int sim_scene_commit(sim_scene *s, int /*device*/) {
     s->hs.build_all();
     s->dmeshes.clear();
     for (auto &m : s->hs.meshes) {
-      DMesh d;
-      d.nodes = reinterpret_cast<const float4 *>(m->nodes.data());
-      d.tris = reinterpret_cast<const float4 *>(m->tri48.data());
-      d.normals = m->normals.data();
-      d.n_nodes = (int32_t)m->nodes.size();
-      d.n_tris = (int32_t)m->tri48.size();
+      const DMesh d = make_dmesh(*m, reinterpret_cast<const float4 *>(m->nodes.data()),
+                                 reinterpret_cast<const float4 *>(m->tri48.data()), m->normals.data());
       s->dmeshes.push_back(d);
     }
     s->ds.objects = s->hs.objects.data();

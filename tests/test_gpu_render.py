@@ -95,7 +95,9 @@ def test_furnace_per_material(pt, which):
     if which in ("lambert", "dielectric", "checker"):
         assert abs(gm - 0.5) < 1e-3 and g.min() > 0.499 and g.max() < 0.501  # KA5: energy conserving -> background
     else:
-        assert gm < 0.5  # these lose energy by construction (material.rs:106-108, tungsten/materials.rs:349-351)
+        # these can only lose energy (material.rs:106-108, tungsten/materials.rs:36,349-351); Metal loses it at grazing
+        # angles only, which the 0.8-radius mask excludes
+        assert gm <= 0.5 + 1e-6 and (which == "metal" or gm < 0.499)
 
 
 def test_sharding_is_invisible(pt):
@@ -168,7 +170,7 @@ def test_device_resident_accumulate_and_resolve(pt):
     stats2 = cs.render_accumulate(s.camera, st, accum.data_ptr(), torch.cuda.current_stream().cuda_stream)  # ADDS
     host, _ = cs.render(s.camera, st)
     assert np.allclose(accum.cpu().numpy().reshape(h, w, 3) / 8.0, host, rtol=1e-5, atol=1e-6)
-    assert stats.extend_launches == stats.iterations > 0 and stats.extend_ms > 0 and stats.shade_ms > 0
+    assert stats.extend_launches >= stats.iterations > 0 and stats.extend_ms > 0 and stats.shade_ms > 0
     assert stats.mesh_rays == 0 and stats2.rays == stats.rays
     out = torch.zeros(w * h, dtype=torch.int32, device="cuda:0")
     assert pt.core().ptc_resolve_device(accum.data_ptr(), w * h, 1.0 / 8.0, out.data_ptr(), torch.cuda.current_stream().cuda_stream) == 0
