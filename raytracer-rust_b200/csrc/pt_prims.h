@@ -25,8 +25,9 @@ PT_HD void set_pos(Hit &h, V3 p) {
 
 // src/objects/sphere.rs:15-53
 PT_HD bool hit_sphere(const float *f, const Ray &ray, float t_min, float t_max, Hit &h) {
-  const V3 center = v3(f[0], f[1], f[2]);
-  const float radius = f[3];
+  const float4 cr = ldg4(reinterpret_cast<const float4 *>(f));
+  const V3 center = v3(cr.x, cr.y, cr.z);
+  const float radius = cr.w;
   const V3 oc = ray.o - center;
   const float a = dot(ray.d, ray.d);
   const float half_b = dot(oc, ray.d);
@@ -62,8 +63,10 @@ PT_HD bool hit_plane(const float *f, const Ray &ray, float t_min, float t_max, H
 
 // src/tungsten/objects/quad.rs:83-132
 PT_HD bool hit_quad(const float *f, const Ray &ray, float t_min, float t_max, Hit &h) {
-  const V3 base = v3(f[0], f[1], f[2]), e0 = v3(f[3], f[4], f[5]), e1 = v3(f[6], f[7], f[8]), n = v3(f[9], f[10], f[11]);
-  const float d = f[12], inv0 = f[13], inv1 = f[14];
+  const float4 *f4 = reinterpret_cast<const float4 *>(f);
+  const float4 q0 = ldg4(f4), q1 = ldg4(f4 + 1), q2 = ldg4(f4 + 2), q3 = ldg4(f4 + 3);
+  const V3 base = v3(q0.x, q0.y, q0.z), e0 = v3(q0.w, q1.x, q1.y), e1 = v3(q1.z, q1.w, q2.x), n = v3(q2.y, q2.z, q2.w);
+  const float d = q3.x, inv0 = q3.y, inv1 = q3.z;
   const float denom = dot(n, ray.d);
   if (fabsf(denom) < kEps) return false;
   const float t = (d - dot(n, ray.o)) / denom;
@@ -82,7 +85,7 @@ PT_HD bool hit_quad(const float *f, const Ray &ray, float t_min, float t_max, Hi
 
 // src/objects/cube.rs:59-158.  f[0..15] = world_to_object, f[16..31] = object_to_world.
 PT_HD bool hit_cube(const float *f, const Ray &ray, float t_min, float t_max, Hit &h) {
-  const float *w2o = f, *o2w = f + 16;
+  const M4 w2o = load_m4(f);
   const V3 o = mat_point(w2o, ray.o);
   const V3 d = mat_vector(w2o, ray.d);  // not renormalised (cube.rs:70-83)
   const float ix = 1.0f / d.x, iy = 1.0f / d.y, iz = 1.0f / d.z;
@@ -109,6 +112,7 @@ PT_HD bool hit_cube(const float *f, const Ray &ray, float t_min, float t_max, Hi
     if (!isinf_f(rcp) && !isnan_f(rcp) && rcp > 0.0f) n = n * rcp;
     else n = v3(0, 0, 0);
   }
+  const M4 o2w = load_m4(f + 16);
   const V3 pw = mat_point(o2w, p);
   const V3 nw = normalized(mat_t_vector(w2o, n));
   if (dot(pw - ray.o, ray.d) < 0.0f) return false;
@@ -125,7 +129,8 @@ PT_HD bool hit_cube(const float *f, const Ray &ray, float t_min, float t_max, Hi
 struct MeshRay {
   V3 o, d_raw, d;
 };
-PT_HD MeshRay mesh_object_ray(const float *w2o, const Ray &ray) {
+PT_HD MeshRay mesh_object_ray(const float *w2o_f, const Ray &ray) {
+  const M4 w2o = load_m4(w2o_f);
   MeshRay r;
   r.o = mat_point(w2o, ray.o);
   r.d_raw = mat_vector(w2o, ray.d);
@@ -148,7 +153,7 @@ PT_HD bool mesh_root_may_hit(const DMesh &mesh, const MeshRay &r, float t_min, f
 // closed-interval recheck on the (quirky) world t.
 PT_HD bool mesh_finish(const float *f, const DMesh &mesh, const Ray &ray, const MeshRay &mr, const MeshHit &mh, float t_min,
                        float t_max, Hit &h) {
-  const float *w2o = f, *o2w = f + 16;
+  const M4 w2o = load_m4(f), o2w = load_m4(f + 16);
   const V3 o = mr.o, d = mr.d;
   const V3 p_obj = o + d * mh.t;  // ray.at(t), bvh.rs:119
   const float4 nq = ldg4(mesh.normals + mh.tri);
