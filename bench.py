@@ -143,7 +143,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--pool", type=int, default=1 << 22, help="path-pool slots")
+    ap.add_argument("--pool", type=int, default=1 << 23, help="path-pool slots")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -283,7 +283,7 @@ def main():
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "parallelism": f"samples x{world}" if world > 1 else "single GPU",
-                       "spp_total": total_spp, "l2": "256 MiB flush write between timed steps", "pool_paths": args.pool or (1 << 20),
+                       "spp_total": total_spp, "l2": "256 MiB flush write between timed steps", "pool_paths": args.pool,
                        "rng": "Philox4x32-10 keyed (pixel, sample, bounce)"},
             "mrays_per_s": rays_all / ms_total / 1e3, "rays_per_path": rays_all / paths_all,
             "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -292,12 +292,14 @@ def main():
             "clocks": clocks,
             "kernel_share": {"extend": ext_ms / render_ms, "shade": shade_ms / render_ms,
                              "other (generate, advance, gaps)": 1.0 - (ext_ms + shade_ms) / render_ms},
-            "roofline": {"kernel": "k_extend", "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+            "roofline": {"kernel": "extend stage = k_extend_pre + k_traverse + k_extend_post (one logical kernel, timed together)", "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": peak_kind,
                          "algorithmic_bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray,
                          "rays_per_launch": rays_per_launch, "avg_launch_ms": ext_ms / max(1, ext_launches),
                          "extend_grays_per_s": rays_rank / ext_s / 1e9 if ext_s > 0 else 0.0,
-                         "note": "BVH + triangle working set is < 1 MB (L1/L2 resident): HBM is the schema's bound, the FP32 view is below"},
+                         "note": "algorithmic bytes = 32 B ray + 16 B hit + 80 B per wide node popped + 48 B per triangle tested (SURVEY.md 8d); "
+                                 "the BVH + triangle working set is < 1 MB (L1/L2 resident), so HBM is the schema's bound, not the binding one: "
+                                 "the stage is instruction-issue bound (profiles/), see roofline_fp32"},
             "roofline_fp32": {"bound": "fp32 issue", "achieved": achieved_tinstr, "peak": fp32_peak, "unit": "Tinstr/s",
                               "frac": achieved_tinstr / fp32_peak, "algorithmic_instr_per_ray": instr_per_ray,
                               "peak_source": f"{sms} SMs x 128 lanes x {sm_mhz:.0f} MHz sampled under load"},

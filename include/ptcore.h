@@ -77,7 +77,7 @@ typedef struct ptc_render_settings {
   int32_t sample_end;
   int32_t tile_mod;     /* pixel sharding: only 32x32 tiles with tile_index % tile_mod == tile_rem; 0 = all */
   int32_t tile_rem;
-  int32_t pool_paths;   /* path-pool slots; 0 = default (1<<20) */
+  int32_t pool_paths;   /* path-pool slots; 0 = default (up to 1<<22, less for small renders) */
   int32_t flags;        /* PTC_FLAG_* */
 } ptc_render_settings;
 

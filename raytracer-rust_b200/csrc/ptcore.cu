@@ -21,6 +21,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <string>
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend_pre(Ctl *ctl, RoundCt
 }
 
 template <bool COUNT>
-__global__ void __launch_bounds__(kExtendThreads) k_traverse(Ctl *ctl, RoundCtl rc, DScene sc, TaskQ tq, int round, float t_min) {
+__global__ void __launch_bounds__(kExtendThreads) k_traverse(Ctl *ctl, RoundCtl rc, DScene sc, TaskQ tq, int round, float t_min, uint32_t refill_lanes) {
   const uint32_t n = rc.n[round];
   const int par = round & 1;
   const uint32_t lane = threadIdx.x & 31u;
@@ -302,7 +303,7 @@ __global__ void __launch_bounds__(kExtendThreads) k_traverse(Ctl *ctl, RoundCtl 
   bool exhausted = n == 0u;
   for (;;) {
     const uint32_t idle = __ballot_sync(0xffffffffu, !active);
-    if (!exhausted && (idle == 0xffffffffu || (uint32_t)__popc(idle) >= kRefillLanes)) {
+    if (!exhausted && (idle == 0xffffffffu || (uint32_t)__popc(idle) >= refill_lanes)) {
       const uint32_t cnt = (uint32_t)__popc(idle);
       uint32_t base = 0;
       if (lane == 0) base = atomicAdd(&rc.cursor[round], cnt);
@@ -667,16 +668,18 @@ namespace {
 // One extend pass = pre, then (traverse, post) once per mesh object a ray can meet.  Returns the number of launches.
 int launch_extend(cudaStream_t stream, int sm_count, Ctl *ctl, const RoundCtl &rc, const DScene &ds, const ExtendOut &eo,
                   const TaskQ &tq, int src, float t_min, float t_max, bool counters) {
-  const dim3 grid(sm_count * 8);
+  static const uint32_t refill = getenv("PTC_REFILL") ? (uint32_t)atoi(getenv("PTC_REFILL")) : kRefillLanes;   // tuning knobs
+  static const int tblocks = getenv("PTC_TBLOCKS") ? atoi(getenv("PTC_TBLOCKS")) : 8;
+  const dim3 grid(sm_count * 8), tgrid(sm_count * tblocks);
   int launches = 1;
   if (counters) k_extend_pre<true><<<grid, kExtendThreads, 0, stream>>>(ctl, rc, ds, eo, tq, src, t_min, t_max);
   else k_extend_pre<false><<<grid, kExtendThreads, 0, stream>>>(ctl, rc, ds, eo, tq, src, t_min, t_max);
   for (int r = 0; r < rc.rounds; r++) {
     if (counters) {
-      k_traverse<true><<<grid, kExtendThreads, 0, stream>>>(ctl, rc, ds, tq, r, t_min);
+      k_traverse<true><<<tgrid, kExtendThreads, 0, stream>>>(ctl, rc, ds, tq, r, t_min, refill);
       k_extend_post<true><<<grid, kExtendThreads, 0, stream>>>(ctl, rc, ds, eo, tq, src, r, t_min, t_max);
     } else {
-      k_traverse<false><<<grid, kExtendThreads, 0, stream>>>(ctl, rc, ds, tq, r, t_min);
+      k_traverse<false><<<tgrid, kExtendThreads, 0, stream>>>(ctl, rc, ds, tq, r, t_min, refill);
       k_extend_post<false><<<grid, kExtendThreads, 0, stream>>>(ctl, rc, ds, eo, tq, src, r, t_min, t_max);
     }
     launches += 2;
@@ -686,8 +689,9 @@ int launch_extend(cudaStream_t stream, int sm_count, Ctl *ctl, const RoundCtl &r
 
 TaskQ taskq_of(ptc_scene *s);
 
+// grow-only: `pool` slots of path state (128 B each) + task queues (96 B each, only for scenes with meshes)
 void ensure_workspace(ptc_scene *s, uint32_t pool) {
-  if (s->pool == pool && s->h_ctl) return;
+  if (s->pool >= pool && s->h_ctl) return;
   for (int k = 0; k < 2; k++) {
     s->w_ray_o[k].alloc(pool);
     s->w_ray_d[k].alloc(pool);
@@ -753,8 +757,14 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
   const int tile_mod = st->tile_mod > 0 ? st->tile_mod : 1;
   const int tile_rem = st->tile_mod > 0 ? st->tile_rem : 0;
   if (tile_rem < 0 || tile_rem >= tile_mod) throw std::invalid_argument("tile_rem out of range");
-  uint32_t pool = st->pool_paths > 0 ? (uint32_t)st->pool_paths : (1u << 20);
-  pool = std::max(pool, 1024u);
+  const uint64_t want_paths = (uint64_t)st->width * st->height * (uint64_t)(s_end - s_begin);
+  uint32_t pool;
+  if (st->pool_paths > 0) {
+    pool = std::max((uint32_t)st->pool_paths, 1024u);
+  } else {  // default: 4 M slots (measured best on B200 for config C2), less for renders that cannot fill them
+    pool = 1u << 16;
+    while (pool < (1u << 22) && pool < want_paths) pool <<= 1;
+  }
   ensure_workspace(s, pool);
 
   RenderParams rp;
