@@ -160,11 +160,23 @@ def main():
     if not torch.cuda.is_available() or pt.device_count() < 1:
         raise SystemExit("bench.py needs a CUDA device: the path tracer has no CPU fallback")
     torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    dev = torch.device("cuda", local)
+        # NCCL prints its version banner on stdout at communicator creation; stdout carries exactly one JSON line,
+        # so park fd 1 on stderr until the communicator exists
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     scene = pt.load_scene_from_json(SCENE)
     w, h, spp, depth = scene.settings

@@ -645,6 +645,8 @@ struct ptc_scene {
   DevBuf<float4> w_tq_o[2], w_tq_d[2];
   DevBuf<float2> w_tq_res[2];
   DevBuf<uint32_t> w_round;  // RoundCtl storage: n[rounds + 1], cursor[rounds + 1]
+  DevBuf<float> w_film, w_film_out;  // ptc_render / ptc_resolve_u32 staging, grow-only
+  DevBuf<uint32_t> w_packed;
   int mesh_objects = 0;  // mesh entries in object_list = extend rounds needed
   DevBuf<Ctl> d_ctl;
   Ctl *h_ctl = nullptr;  // pinned ring
@@ -1092,9 +1094,9 @@ int ptc_render(ptc_scene *s, const ptc_camera *cam, const ptc_render_settings *s
   if (st->width <= 0 || st->height <= 0 || st->spp <= 0) throw std::invalid_argument("bad render settings");
   CK(cudaSetDevice(s->device));
   const size_t n = (size_t)st->width * st->height * 3;
-  DevBuf<float> accum, out;
-  accum.alloc(n);
-  out.alloc(n);
+  if (s->w_film.n < n) s->w_film.alloc(n);
+  if (s->w_film_out.n < n) s->w_film_out.alloc(n);
+  DevBuf<float> &accum = s->w_film, &out = s->w_film_out;
   cudaStream_t stream = s->own_stream;
   CK(cudaMemsetAsync(accum.p, 0, n * sizeof(float), stream));
   render_accumulate(s, cam, st, accum.p, stream, stats);
@@ -1124,10 +1126,11 @@ int ptc_resolve_u32(ptc_scene *s, const float *rgb, int64_t n_pixels, float scal
   if (!rgb || !out || n_pixels < 0) throw std::invalid_argument("bad argument");
   if (n_pixels == 0) return 0;
   CK(cudaSetDevice(s->device));
-  DevBuf<float> d_in;
-  DevBuf<uint32_t> d_out;
-  d_in.upload(rgb, (size_t)n_pixels * 3);
-  d_out.alloc((size_t)n_pixels);
+  if (s->w_film_out.n < (size_t)n_pixels * 3) s->w_film_out.alloc((size_t)n_pixels * 3);
+  if (s->w_packed.n < (size_t)n_pixels) s->w_packed.alloc((size_t)n_pixels);
+  DevBuf<float> &d_in = s->w_film_out;
+  DevBuf<uint32_t> &d_out = s->w_packed;
+  CK(cudaMemcpyAsync(d_in.p, rgb, (size_t)n_pixels * 3 * sizeof(float), cudaMemcpyHostToDevice, s->own_stream));
   k_resolve<<<(unsigned)((n_pixels + 255) / 256), 256, 0, s->own_stream>>>(d_in.p, (size_t)n_pixels, scale, d_out.p);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, d_out.p, (size_t)n_pixels * 4, cudaMemcpyDeviceToHost, s->own_stream));
