@@ -109,6 +109,8 @@ typedef struct ptc_stats {
   uint64_t nodes_visited;  /* wide-BVH nodes popped   (only with PTC_FLAG_COUNTERS) */
   uint64_t tris_tested;    /* triangles tested        (only with PTC_FLAG_COUNTERS) */
   uint64_t mesh_rays;      /* ray x mesh-instance traversals (only with PTC_FLAG_COUNTERS) */
+  double pre_ms, traverse_ms, post_ms; /* the three kernels of the extend stage (PTC_FLAG_TIMING); extend_ms = their sum */
+  double regen_ms;         /* k_advance + k_generate (PTC_FLAG_TIMING) */
 } ptc_stats;
 
 typedef struct ptc_mesh_info {

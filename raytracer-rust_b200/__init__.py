@@ -56,7 +56,8 @@ class Stats(C.Structure):  # ptc_stats
     _fields_ = [("paths", C.c_uint64), ("rays", C.c_uint64), ("iterations", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("render_ms", C.c_double), ("extend_ms", C.c_double), ("shade_ms", C.c_double),
                 ("extend_launches", C.c_uint64), ("nodes_visited", C.c_uint64), ("tris_tested", C.c_uint64),
-                ("mesh_rays", C.c_uint64)]
+                ("mesh_rays", C.c_uint64), ("pre_ms", C.c_double), ("traverse_ms", C.c_double), ("post_ms", C.c_double),
+                ("regen_ms", C.c_double)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -239,7 +239,7 @@ QFrame make_frame(const Box3 &box) {
     std::frexp(need, &ex);  // need = m * 2^ex, m in [0.5, 1)  =>  2^ex >= need
     int biased = ex + 127;
     if (biased < 1) biased = 1;
-    if (biased > 254) throw std::runtime_error("mesh extent too large for the quantised BVH frame");
+    if (biased > 254 - 15) throw std::runtime_error("mesh extent too large for the quantised BVH frame");  // trav_node adds 15
     f.origin[a] = flo;
     f.biased_exp[a] = biased;
     f.scale[a] = std::ldexp(1.0, biased - 127);

@@ -38,6 +38,19 @@ PT_HD float box_rcp(float x) {
 #endif
 }
 
+// Byte j of `packed` as the float 1 + byte * 2^-15, built by ONE byte permute (no int->float conversion: I2F runs at
+// an eighth of the FP32 rate on sm_100 and there are 48 of them per node).  The slab arithmetic absorbs the affine
+// map: q * adj + org == m * (adj * 2^15) + (org - adj * 2^15) with m = 1 + q * 2^-15; the extra rounding error is
+// ~2^-17 of the node's t-extent, far inside the 2^-9 padding the builder gives every frame.
+template <int J>
+PT_HD float byte_as_unit_float(uint32_t packed) {
+#if defined(__CUDA_ARCH__)
+  return __uint_as_float(__byte_perm(packed, 0x3F800000u, 0x7604u | (uint32_t)(J << 4)));
+#else
+  return u2f(0x3F800000u | (((packed >> (8 * J)) & 0xffu) << 8));
+#endif
+}
+
 struct TravState {
   V3 o, d;             // object-space ray
   float idx, idy, idz;  // 1/d for the slab tests
@@ -79,10 +92,11 @@ PT_HD void trav_node(const DMesh &m, TravState &s, uint2 *stack, int &sp, Traver
   if (COUNT) ctr->nodes++;
 
   const uint32_t e = f2u(q0.w);
-  const float adjx = u2f((e & 0xffu) << 23) * s.idx;
-  const float adjy = u2f(((e >> 8) & 0xffu) << 23) * s.idy;
-  const float adjz = u2f(((e >> 16) & 0xffu) << 23) * s.idz;
-  const float orgx = (q0.x - s.o.x) * s.idx, orgy = (q0.y - s.o.y) * s.idy, orgz = (q0.z - s.o.z) * s.idz;
+  // scale * 2^15 folded into the exponent byte (the builder keeps biased exponents <= 254 - 15)
+  const float adjx = u2f(((e & 0xffu) + 15u) << 23) * s.idx;
+  const float adjy = u2f((((e >> 8) & 0xffu) + 15u) << 23) * s.idy;
+  const float adjz = u2f((((e >> 16) & 0xffu) + 15u) << 23) * s.idz;
+  const float orgx = (q0.x - s.o.x) * s.idx - adjx, orgy = (q0.y - s.o.y) * s.idy - adjy, orgz = (q0.z - s.o.z) * s.idz - adjz;
 
   // near / far planes by ray octant
   const bool sx = (f2u(s.d.x) >> 31) != 0u, sy = (f2u(s.d.y) >> 31) != 0u, sz = (f2u(s.d.z) >> 31) != 0u;
@@ -103,20 +117,21 @@ PT_HD void trav_node(const DMesh &m, TravState &s, uint2 *stack, int &sp, Traver
     const uint32_t inner_mask4 = (is_inner4 >> 4) * 0xffu;
     const uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1f1f1f1fu;
     const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const int sh = 8 * j;
-      const float tnx = fmaf((float)((nx[h] >> sh) & 0xffu), adjx, orgx);
-      const float tny = fmaf((float)((ny[h] >> sh) & 0xffu), adjy, orgy);
-      const float tnz = fmaf((float)((nz[h] >> sh) & 0xffu), adjz, orgz);
-      const float tfx = fmaf((float)((fx[h] >> sh) & 0xffu), adjx, orgx);
-      const float tfy = fmaf((float)((fy[h] >> sh) & 0xffu), adjy, orgy);
-      const float tfz = fmaf((float)((fz[h] >> sh) & 0xffu), adjz, orgz);
-      // fmaxf / fminf drop NaN operands (0 * inf from axis-parallel rays): the slab then does not constrain
-      const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, s.t_min));
-      const float tf = fminf(fminf(tfx, tfy), fminf(tfz, s.best_t));
-      if (tn <= tf) hitmask |= ((child_bits4 >> sh) & 0xffu) << ((bit_index4 >> sh) & 0xffu);
-    }
+#define PT_CHILD(J)                                                                                       \
+  {                                                                                                       \
+    const float tnx = fmaf(byte_as_unit_float<J>(nx[h]), adjx, orgx);                                     \
+    const float tny = fmaf(byte_as_unit_float<J>(ny[h]), adjy, orgy);                                     \
+    const float tnz = fmaf(byte_as_unit_float<J>(nz[h]), adjz, orgz);                                     \
+    const float tfx = fmaf(byte_as_unit_float<J>(fx[h]), adjx, orgx);                                     \
+    const float tfy = fmaf(byte_as_unit_float<J>(fy[h]), adjy, orgy);                                     \
+    const float tfz = fmaf(byte_as_unit_float<J>(fz[h]), adjz, orgz);                                     \
+    /* fmaxf / fminf drop NaN operands (0 * inf from axis-parallel rays): the slab then does not constrain */ \
+    const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, s.t_min));                                          \
+    const float tf = fminf(fminf(tfx, tfy), fminf(tfz, s.best_t));                                         \
+    if (tn <= tf) hitmask |= ((child_bits4 >> (8 * J)) & 0xffu) << ((bit_index4 >> (8 * J)) & 0xffu);      \
+  }
+    PT_CHILD(0) PT_CHILD(1) PT_CHILD(2) PT_CHILD(3)
+#undef PT_CHILD
   }
   s.ng.x = f2u(q1.x);
   s.ng.y = (hitmask & 0xFF000000u) | (e >> 24);

@@ -24,6 +24,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -405,30 +406,88 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend_post(Ctl *ctl, RoundC
 
 constexpr int kShadeThreads = 256;
 constexpr int kShadeClasses = 10;  // 0 = miss, 1 + material type (8 types), 9 = no ray (tail of the last chunk)
+constexpr int kShadeArrays = 5;    // ray_o, ray_d, beta, hit0, hit1
+constexpr size_t kShadeSmem = 2 * kShadeArrays * kShadeThreads * sizeof(float4) + 128;  // two staged chunks + alignment slack
+
+// ---- sm_100a asynchronous bulk copy (TMA, 1-D) + mbarrier, raw PTX ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// global -> shared, completion (byte count) signalled on the mbarrier; SASS: UBLKCP
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 
 // shade: emitted + scatter (renderer.rs:26-36) or sky (renderer.rs:38-63); compacts survivors into buffer `dst`.
 //
 // Rays arrive in no particular order, so a warp would see a mix of misses and of every material and run all of their
-// code (measured: 11.5 of 32 lanes active).  Each block therefore takes a chunk of 256 consecutive rays: every thread
-// loads ITS ray's state with five independent, fully coalesced 16-byte loads, the block counting-sorts the chunk by
-// (miss | material type) in shared memory, and the state is handed through shared memory to the thread that shades
-// it — thread t shades the t-th ray of the sorted order, so warps are homogeneous except where a class boundary falls
-// inside them, and global memory is touched once per ray, in order.
+// code (measured: 11.5 of 32 lanes active), and the kernel is latency-bound if each thread waits for its own loads.
+// Each persistent block therefore walks chunks of 256 consecutive rays with a two-stage pipeline:
+//   * one thread issues five 1-D bulk async copies (TMA; ray_o, ray_d, beta, hit0, hit1 slices, 4 KB each) of the NEXT
+//     chunk into shared memory, completion counted on an mbarrier, while the block shades the current one;
+//   * the current chunk is counting-sorted by (miss | material type) in shared memory (10 ballots per warp + one
+//     10-lane scan); thread t then shades the t-th ray of that order straight out of the staged copy, so warps are
+//     homogeneous except where a class boundary falls inside them (26 of 32 lanes active after, 11.5 before);
+//   * survivors are compacted into the other ray buffer with one atomic per warp.
 __global__ void __launch_bounds__(kShadeThreads, 3) k_shade(Ctl *ctl, DScene sc, RenderParams rp, Buffers b, int src, int dst, float *accum) {
-  __shared__ float4 s_state[5][kShadeThreads];  // ray_o, ray_d, beta, hit0, hit1 of the chunk, in sorted order
+  extern __shared__ uint8_t s_dyn[];
+  float4 *s_raw = reinterpret_cast<float4 *>((reinterpret_cast<uintptr_t>(s_dyn) + 127) & ~(uintptr_t)127);  // [2][5][256]
+  __shared__ uint16_t s_perm[kShadeThreads];
   __shared__ uint32_t s_cnt[kShadeThreads / 32][kShadeClasses];
   __shared__ uint32_t s_off[kShadeThreads / 32][kShadeClasses];
+  __shared__ __align__(8) uint64_t s_bar[2];
   const uint32_t n = ctl->n_cur;
+  const uint32_t n_chunks = (n + (uint32_t)kShadeThreads - 1) / (uint32_t)kShadeThreads;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-  for (uint32_t chunk = blockIdx.x * (uint32_t)kShadeThreads; chunk < n; chunk += gridDim.x * (uint32_t)kShadeThreads) {
-    const uint32_t in_chunk = n - chunk < (uint32_t)kShadeThreads ? n - chunk : (uint32_t)kShadeThreads;
+  const float4 *g_arr[kShadeArrays] = {b.ray_o[src], b.ray_d[src], b.beta[src], b.hit0, b.hit1};
+
+  auto issue = [&](uint32_t chunk, uint32_t buf) {  // one thread
+    const uint32_t first = chunk * (uint32_t)kShadeThreads;
+    const uint32_t cnt = n - first < (uint32_t)kShadeThreads ? n - first : (uint32_t)kShadeThreads;
+    const uint32_t bytes = cnt * (uint32_t)sizeof(float4);
+    mbar_expect_tx(&s_bar[buf], bytes * kShadeArrays);
+#pragma unroll
+    for (int a = 0; a < kShadeArrays; a++)
+      bulk_g2s(s_raw + ((size_t)buf * kShadeArrays + a) * kShadeThreads, g_arr[a] + first, bytes, &s_bar[buf]);
+  };
+
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0 && blockIdx.x < n_chunks) issue(blockIdx.x, 0);
+
+  uint32_t k = 0;
+  for (uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x, k++) {
+    const uint32_t buf = k & 1u;
+    // the other stage was last read in the previous iteration, which ended with a block barrier
+    if (tid == 0 && chunk + gridDim.x < n_chunks) issue(chunk + gridDim.x, buf ^ 1u);
+    const uint32_t first = chunk * (uint32_t)kShadeThreads;
+    const uint32_t in_chunk = n - first < (uint32_t)kShadeThreads ? n - first : (uint32_t)kShadeThreads;
+    const float4 *raw = s_raw + (size_t)buf * kShadeArrays * kShadeThreads;
+    mbar_wait(&s_bar[buf], (k >> 1) & 1u);
+
     uint32_t key = kShadeClasses - 1;
-    float4 o4, d4, b4, h0, h1;
     if (tid < in_chunk) {
-      const uint32_t g = chunk + tid;
-      o4 = b.ray_o[src][g], d4 = b.ray_d[src][g], b4 = b.beta[src][g], h1 = b.hit1[g];
-      const uint32_t bits0 = f2u(h1.w);
-      h0 = (bits0 & kHitBit) ? b.hit0[g] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);  // extend leaves hit0 unwritten on a miss
+      const uint32_t bits0 = f2u(raw[4 * kShadeThreads + tid].w);
       key = (bits0 & kHitBit) ? 1u + (uint32_t)sc.materials[bits0 & kMatMask].type : 0u;
     }
     uint32_t rank = 0;
@@ -458,16 +517,15 @@ __global__ void __launch_bounds__(kShadeThreads, 3) k_shade(Ctl *ctl, DScene sc,
       }
     }
     __syncthreads();
-    if (tid < in_chunk) {
-      const uint32_t pos = s_off[warp][key] + rank;
-      s_state[0][pos] = o4, s_state[1][pos] = d4, s_state[2][pos] = b4, s_state[3][pos] = h0, s_state[4][pos] = h1;
-    }
+    s_perm[s_off[warp][key] + rank] = (uint16_t)tid;
     __syncthreads();
 
     bool alive = false;
     float4 no, nd, nb;
     if (tid < in_chunk) {  // the "no ray" class sorts last
-      o4 = s_state[0][tid], d4 = s_state[1][tid], b4 = s_state[2][tid], h1 = s_state[4][tid];
+      const uint32_t j = s_perm[tid];
+      const float4 o4 = raw[0 * kShadeThreads + j], d4 = raw[1 * kShadeThreads + j], b4 = raw[2 * kShadeThreads + j];
+      const float4 h1 = raw[4 * kShadeThreads + j];
       const uint32_t pixel = f2u(o4.w), sample = f2u(d4.w), bounce = f2u(b4.w);
       const uint32_t bits = f2u(h1.w);
       const V3 beta = v3(b4.x, b4.y, b4.z);
@@ -478,7 +536,7 @@ __global__ void __launch_bounds__(kShadeThreads, 3) k_shade(Ctl *ctl, DScene sc,
         radiance = beta * sky_color(sc, ray_d);
         add = true;
       } else {
-        h0 = s_state[3][tid];
+        const float4 h0 = raw[3 * kShadeThreads + j];
         const DMaterial m = sc.materials[bits & kMatMask];
         const V3 e = mat_emitted(m);
         if (e.x != 0.0f || e.y != 0.0f || e.z != 0.0f) {
@@ -518,7 +576,7 @@ __global__ void __launch_bounds__(kShadeThreads, 3) k_shade(Ctl *ctl, DScene sc,
         b.beta[dst][slot] = nb;
       }
     }
-    __syncthreads();  // s_state is reused by the next chunk
+    __syncthreads();  // stage `buf` and s_perm are free again
   }
 }
 
@@ -668,22 +726,25 @@ struct ptc_scene {
 namespace {
 
 // One extend pass = pre, then (traverse, post) once per mesh object a ray can meet.  Returns the number of launches.
+enum Stage { ST_PRE = 0, ST_TRAVERSE, ST_POST, ST_SHADE, ST_REGEN, ST_COUNT };
+
 int launch_extend(cudaStream_t stream, int sm_count, Ctl *ctl, const RoundCtl &rc, const DScene &ds, const ExtendOut &eo,
-                  const TaskQ &tq, int src, float t_min, float t_max, bool counters) {
+                  const TaskQ &tq, int src, float t_min, float t_max, bool counters,
+                  const std::function<void(int)> *mark = nullptr) {
   static const uint32_t refill = getenv("PTC_REFILL") ? (uint32_t)atoi(getenv("PTC_REFILL")) : kRefillLanes;   // tuning knobs
   static const int tblocks = getenv("PTC_TBLOCKS") ? atoi(getenv("PTC_TBLOCKS")) : 8;
   const dim3 grid(sm_count * 8), tgrid(sm_count * tblocks);
   int launches = 1;
+  if (mark) (*mark)(ST_PRE);
   if (counters) k_extend_pre<true><<<grid, kExtendThreads, 0, stream>>>(ctl, rc, ds, eo, tq, src, t_min, t_max);
   else k_extend_pre<false><<<grid, kExtendThreads, 0, stream>>>(ctl, rc, ds, eo, tq, src, t_min, t_max);
   for (int r = 0; r < rc.rounds; r++) {
-    if (counters) {
-      k_traverse<true><<<tgrid, kExtendThreads, 0, stream>>>(ctl, rc, ds, tq, r, t_min, refill);
-      k_extend_post<true><<<grid, kExtendThreads, 0, stream>>>(ctl, rc, ds, eo, tq, src, r, t_min, t_max);
-    } else {
-      k_traverse<false><<<tgrid, kExtendThreads, 0, stream>>>(ctl, rc, ds, tq, r, t_min, refill);
-      k_extend_post<false><<<grid, kExtendThreads, 0, stream>>>(ctl, rc, ds, eo, tq, src, r, t_min, t_max);
-    }
+    if (mark) (*mark)(ST_TRAVERSE);
+    if (counters) k_traverse<true><<<tgrid, kExtendThreads, 0, stream>>>(ctl, rc, ds, tq, r, t_min, refill);
+    else k_traverse<false><<<tgrid, kExtendThreads, 0, stream>>>(ctl, rc, ds, tq, r, t_min, refill);
+    if (mark) (*mark)(ST_POST);
+    if (counters) k_extend_post<true><<<grid, kExtendThreads, 0, stream>>>(ctl, rc, ds, eo, tq, src, r, t_min, t_max);
+    else k_extend_post<false><<<grid, kExtendThreads, 0, stream>>>(ctl, rc, ds, eo, tq, src, r, t_min, t_max);
     launches += 2;
   }
   return launches;
@@ -816,6 +877,11 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
     return s->timing_events[tev_used++];
   };
 
+  std::vector<int> mark_stage;
+  const std::function<void(int)> mark = [&](int stage) {
+    CK(cudaEventRecord(tev(), stream));
+    mark_stage.push_back(stage);
+  };
   CK(cudaEventRecord(ev_begin, stream));
   int cur = 0;
   k_advance<<<1, 32, 0, stream>>>(s->d_ctl.p, rc, pool);
@@ -827,12 +893,11 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
   const int check_every = 4;
   bool finished = init.total_paths == 0;
   while (!finished) {
-    if (timing) CK(cudaEventRecord(tev(), stream));
     const ExtendOut eo{b, nullptr};
-    launches += launch_extend(stream, sms, s->d_ctl.p, rc, s->ds, eo, tq, cur, kEps, INFINITY, counters) - 1;
-    if (timing) CK(cudaEventRecord(tev(), stream));
-    k_shade<<<g_shade, kShadeThreads, 0, stream>>>(s->d_ctl.p, s->ds, rp, b, cur, cur ^ 1, d_accum);
-    if (timing) CK(cudaEventRecord(tev(), stream));
+    launches += launch_extend(stream, sms, s->d_ctl.p, rc, s->ds, eo, tq, cur, kEps, INFINITY, counters, timing ? &mark : nullptr) - 1;
+    if (timing) mark(ST_SHADE);
+    k_shade<<<g_shade, kShadeThreads, kShadeSmem, stream>>>(s->d_ctl.p, s->ds, rp, b, cur, cur ^ 1, d_accum);
+    if (timing) mark(ST_REGEN);
     k_advance<<<1, 32, 0, stream>>>(s->d_ctl.p, rc, pool);
     k_generate<<<g_gen, 256, 0, stream>>>(s->d_ctl.p, rp, b, cur ^ 1);
     launches += 4;
@@ -879,18 +944,21 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
     CK(cudaEventElapsedTime(&ms, ev_begin, ev_end));
     stats->render_ms = ms;
     if (timing) {
-      double ext = 0.0, shd = 0.0;
+      // every mark opens a stage that lasts until the next mark (the last one until the end-of-render event)
+      double per[ST_COUNT] = {0, 0, 0, 0, 0};
       uint64_t n_ext = 0;
-      for (size_t k = 0; k + 3 <= tev_used; k += 3) {
-        float a = 0.0f, c = 0.0f;
-        CK(cudaEventElapsedTime(&a, s->timing_events[k], s->timing_events[k + 1]));
-        CK(cudaEventElapsedTime(&c, s->timing_events[k + 1], s->timing_events[k + 2]));
-        ext += a;
-        shd += c;
-        n_ext++;
+      for (size_t k = 0; k < tev_used; k++) {
+        float a = 0.0f;
+        CK(cudaEventElapsedTime(&a, s->timing_events[k], k + 1 < tev_used ? s->timing_events[k + 1] : ev_end));
+        per[mark_stage[k]] += a;
+        if (mark_stage[k] == ST_PRE) n_ext++;
       }
-      stats->extend_ms = ext;
-      stats->shade_ms = shd;
+      stats->pre_ms = per[ST_PRE];
+      stats->traverse_ms = per[ST_TRAVERSE];
+      stats->post_ms = per[ST_POST];
+      stats->extend_ms = per[ST_PRE] + per[ST_TRAVERSE] + per[ST_POST];
+      stats->shade_ms = per[ST_SHADE];
+      stats->regen_ms = per[ST_REGEN];
       stats->extend_launches = n_ext;
     }
     stats->nodes_visited = fin.nodes;

@@ -75,6 +75,10 @@ pub struct ptc_stats {
     pub nodes_visited: u64,
     pub tris_tested: u64,
     pub mesh_rays: u64,
+    pub pre_ms: f64,
+    pub traverse_ms: f64,
+    pub post_ms: f64,
+    pub regen_ms: f64,
 }
 
 #[repr(C)]
