@@ -1,0 +1,637 @@
+// pt_wavefront.cuh — the wavefront kernels of the B200 path-tracing core (included by ptcore.cu only).
+//
+// trace_ray's recursion  L = Le + f * trace(next)  (src/renderer.rs:19-65 of the reference) is unrolled into a
+// SEGMENTED wavefront.  The path pool is cut into S segments of `cap` slots, S = resident blocks of the GPU; block b of
+// every kernel owns segment b and nothing else:
+//
+//   k_extend_pre   analytic primitives of the object list up to the first mesh whose root-frame test passes; such a
+//                  ray is PARKED as a task in the block's task segment (shared-memory cursor)
+//   k_traverse     persistent warps over the block's tasks: each lane walks its own BVH one step at a time, idle lanes
+//                  refetch from the block's cursor
+//   k_extend_post  second half of Mesh::hit + rest of the object list for every task; may park again (next round)
+//   k_shade        stages 256-ray chunks of the segment through shared memory with TMA bulk copies, counting-sorts each
+//                  chunk by material, shades, writes the survivors back IN PLACE at the front of the segment, then
+//                  REGENERATES: tops the segment up with fresh camera paths (Philox jitter + Camera::get_ray)
+//
+// Consequences: no global compaction, no global queue cursor — the only same-address global atomics left are one
+// `next_path` reservation and one `n_live` add per block and iteration (per-warp atomics on single counters were 16-56 %
+// of the stall samples of the previous design, profiles/r1_v3_*); ray state is single-buffered; each block's working
+// set stays in its own slice of memory; when the path supply runs out all segments drain together, so the tail needs
+// no repacking either.
+//
+// Only Emissive surfaces and the sky carry radiance and both end the path (EmissiveLight::scatter is None), so a path
+// contributes beta * Le exactly once, when it terminates: one float RED triple per path into the film.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/ptcore.h"
+#include "pt_bsdf.h"
+#include "pt_philox.h"
+#include "pt_prims.h"
+
+namespace ptw {
+using namespace pt;
+
+constexpr int kBlock = 256;    // threads per block of every stage kernel
+constexpr int kSegPerSM = 4;   // segments (= resident blocks) per SM: 4 x 256 threads x <= 64 registers
+constexpr uint32_t kRefillLanes = 8;  // a traversal warp fetches new tasks once this many lanes are idle
+
+// Device-side control block of one render
+struct Ctl {
+  unsigned long long next_path;    // next camera path index to hand out
+  unsigned long long total_paths;  // path index space of this call (padded tiles x samples)
+  unsigned long long rays;         // extend items so far = trace_ray calls with depth > 0
+  unsigned long long nodes, tris, mesh_rays;  // PTC_FLAG_COUNTERS
+  uint32_t n_live;      // rays alive after the last shade (sum of the segment counts)
+  uint32_t iterations;
+};
+
+struct RenderParams {
+  DCamera cam;
+  int32_t width, height;
+  int32_t max_depth;
+  int32_t sample_begin, n_samples;
+  int32_t tiles_x, n_my_tiles, tile_mod, tile_rem;
+  uint32_t row_mult;  // odd, coprime with n_my_tiles: scatters consecutive 32-pixel rows over the image (see k_shade)
+  uint64_t seed;
+};
+
+// Path state, SoA of float4.  Segment b = slots [b * cap, b * cap + cnt[b]).
+struct Buffers {
+  float4 *ray_o;  // origin.xyz, pixel index
+  float4 *ray_d;  // direction.xyz, sample index
+  float4 *beta;   // throughput.rgb, bounce (segments already traced)
+  float4 *hit0;   // position.xyz, t
+  float4 *hit1;   // normal.xyz, [hit<<31 | front_face<<30 | material]
+  uint32_t *cnt;  // [S]
+  uint32_t cap;   // multiple of kBlock
+};
+
+struct ExtendOut {
+  Buffers b;
+  int2 *ids;  // (object, triangle) per ray, only for ptc_intersect (nullptr in renders)
+};
+
+// Parked-ray tasks, [round & 1]; block b's tasks of round r = slots [b * cap, b * cap + cnt[r * S + b])
+struct TaskQ {
+  uint2 *ray[2];   // x = ray slot, y = object index of the mesh
+  float4 *o[2];    // object-space origin, closest_so_far (the t_max Mesh::hit was called with)
+  float4 *d[2];    // object-space direction (normalised twice, mesh_object.rs:287 + ray.rs:15)
+  float2 *res[2];  // traversal result: t (object space), original triangle index or 0xffffffff
+  uint32_t *cnt;   // [(rounds + 1) * S]
+};
+
+constexpr uint32_t kHitBit = 0x80000000u, kFrontBit = 0x40000000u, kMatMask = 0x3fffffffu;
+
+__device__ __forceinline__ void write_hit(const ExtendOut &out, uint32_t i, const Hit &h) {
+  out.b.hit0[i] = make_float4(h.px, h.py, h.pz, h.t);
+  out.b.hit1[i] = make_float4(h.nx, h.ny, h.nz, u2f(kHitBit | (h.front_face ? kFrontBit : 0u) | ((uint32_t)h.material & kMatMask)));
+  if (out.ids) out.ids[i] = make_int2(h.object, h.triangle);
+}
+__device__ __forceinline__ void write_miss(const ExtendOut &out, uint32_t i) {
+  out.b.hit1[i] = make_float4(0.0f, 0.0f, 0.0f, u2f(0u));
+  if (out.ids) out.ids[i] = make_int2(-1, -1);
+}
+
+// HittableList::hit (hittable.rs:46-57) over objects [k_begin, n): insertion order, shrinking t_max, each primitive's own
+// interval convention.  Returns the index of the mesh the ray has to be parked at (its object-space ray in
+// `park_ray`), or -1 when the scan is complete.  Every object sees exactly the `closest` it would have seen in the
+// reference's sequential scan, so tie-breaking is untouched by the parking.
+__device__ __forceinline__ int scan_objects(const DScene &sc, const Ray &ray, float t_min, float &closest, Hit &best,
+                                            bool &improved, int k_begin, MeshRay &park_ray) {
+  for (int k = k_begin; k < sc.n_objects; k++) {
+    const DObject *ob = sc.objects + k;
+    const int type = ob->type;
+    Hit tmp;
+    tmp.triangle = -1;
+    bool hit;
+    if (type == OBJ_MESH) {
+      const MeshRay mr = mesh_object_ray(ob->f, ray);
+      if (!mesh_root_may_hit(sc.meshes[ob->mesh], mr, t_min, closest)) continue;  // same as Mesh::hit returning None
+      park_ray = mr;
+      return k;
+    }
+    if (type == OBJ_SPHERE) hit = hit_sphere(ob->f, ray, t_min, closest, tmp);
+    else if (type == OBJ_QUAD) hit = hit_quad(ob->f, ray, t_min, closest, tmp);
+    else if (type == OBJ_CUBE) hit = hit_cube(ob->f, ray, t_min, closest, tmp);
+    else hit = hit_plane(ob->f, ray, t_min, closest, tmp);
+    if (hit) {
+      improved = true;
+      closest = tmp.t;
+      best = tmp;
+      best.object = k;
+      best.material = ob->material;
+    }
+  }
+  return -1;
+}
+
+// Append the parked lanes of this warp to the block's task segment: ballot + one SHARED-memory atomic per warp.
+__device__ __forceinline__ void park_tasks(uint32_t *s_ntask, const TaskQ &tq, int par, uint32_t seg_base, int park, uint32_t i,
+                                           const MeshRay &mr, float closest) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t mask = __ballot_sync(0xffffffffu, park >= 0);
+  if (mask == 0u) return;
+  uint32_t slot0 = 0;
+  if (lane == 0) slot0 = atomicAdd(s_ntask, (uint32_t)__popc(mask));
+  slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+  if (park >= 0) {
+    const uint32_t slot = seg_base + slot0 + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+    tq.ray[par][slot] = make_uint2(i, (uint32_t)park);
+    tq.o[par][slot] = make_float4(mr.o.x, mr.o.y, mr.o.z, closest);
+    tq.d[par][slot] = make_float4(mr.d.x, mr.d.y, mr.d.z, 0.0f);
+  }
+}
+
+__global__ void __launch_bounds__(kBlock, kSegPerSM) k_extend_pre(Ctl *ctl, DScene sc, ExtendOut out, TaskQ tq, float t_min, float t_max) {
+  __shared__ uint32_t s_ntask;
+  const uint32_t seg = blockIdx.x, tid = threadIdx.x;
+  const uint32_t n = out.b.cnt[seg], seg_base = seg * out.b.cap;
+  if (tid == 0) {
+    s_ntask = 0;
+    if (seg == 0) {  // iteration bookkeeping (the previous shade has finished: kernels of a stream run in order)
+      const uint32_t live = ctl->n_live;
+      ctl->rays += live;
+      if (live) ctl->iterations++;
+      ctl->n_live = 0;
+    }
+  }
+  __syncthreads();
+  for (uint32_t c0 = 0; c0 < n; c0 += (uint32_t)kBlock) {
+    const uint32_t i = seg_base + c0 + tid;
+    int park = -1;
+    MeshRay mr;
+    float closest = t_max;
+    if (c0 + tid < n) {
+      const float4 o4 = out.b.ray_o[i], d4 = out.b.ray_d[i];
+      const Ray ray{v3(o4.x, o4.y, o4.z), v3(d4.x, d4.y, d4.z)};
+      Hit best;
+      bool improved = false;
+      park = scan_objects(sc, ray, t_min, closest, best, improved, 0, mr);  // renderer.rs:24
+      if (improved) write_hit(out, i, best);
+      else write_miss(out, i);
+    }
+    park_tasks(&s_ntask, tq, 0, seg_base, park, i, mr, closest);
+  }
+  __syncthreads();
+  if (tid == 0 && tq.cnt) tq.cnt[seg] = s_ntask;
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlock, kSegPerSM) k_traverse(Ctl *ctl, DScene sc, TaskQ tq, int round, float t_min, uint32_t cap,
+                                                                uint32_t refill_lanes) {
+  __shared__ uint32_t s_cur;
+  const uint32_t seg = blockIdx.x;
+  const uint32_t n = tq.cnt[(uint32_t)round * gridDim.x + seg], seg_base = seg * cap;
+  const int par = round & 1;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  if (threadIdx.x == 0) s_cur = 0;
+  __syncthreads();
+  TraversalCounters tc{0u, 0u, 0u};
+  TravState s;
+  DMesh mesh;  // the two pointers of the mesh this lane walks, kept in registers
+  mesh.nodes = nullptr, mesh.tris = nullptr;
+  uint2 stack[kTraversalStack];
+  int sp = 0;
+  bool active = false;
+  uint32_t task = 0;
+  bool exhausted = n == 0u;
+  for (;;) {
+    const uint32_t idle = __ballot_sync(0xffffffffu, !active);
+    if (!exhausted && (idle == 0xffffffffu || (uint32_t)__popc(idle) >= refill_lanes)) {
+      const uint32_t cnt = (uint32_t)__popc(idle);
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(&s_cur, cnt);  // shared memory: the block's own cursor
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (!active) {
+        const uint32_t j = base + (uint32_t)__popc(idle & lt_mask);
+        if (j < n) {
+          const uint32_t slot = seg_base + j;
+          const uint2 rk = tq.ray[par][slot];
+          const float4 o4 = tq.o[par][slot], d4 = tq.d[par][slot];
+          const DMesh *gm = sc.meshes + sc.objects[rk.y].mesh;
+          mesh.nodes = gm->nodes;
+          mesh.tris = gm->tris;
+          trav_begin(s, v3(o4.x, o4.y, o4.z), v3(d4.x, d4.y, d4.z), t_min, o4.w);  // world t bounds, mesh_object.rs:289-291
+          sp = 0;
+          task = slot;
+          active = true;
+          if (COUNT) tc.mesh_rays++;
+        }
+      }
+      if (base + cnt >= n) exhausted = true;
+    }
+    if (__ballot_sync(0xffffffffu, active) == 0u) {
+      if (exhausted) break;
+      continue;
+    }
+    if (active) {
+      if (!trav_has_tri(s) && !trav_has_node(s)) {
+        if (sp > 0) {
+          s.ng = stack[--sp];
+        } else {
+          tq.res[par][task] = make_float2(s.best_t, u2f(s.best_tri));
+          active = false;
+        }
+      }
+      if (active && !trav_has_tri(s) && trav_has_node(s)) trav_node<COUNT>(mesh, s, stack, sp, &tc);
+      if (active && trav_has_tri(s)) trav_tri<COUNT>(mesh, s, &tc);
+    }
+  }
+  if (COUNT) {
+    atomicAdd(&ctl->nodes, (unsigned long long)tc.nodes);
+    atomicAdd(&ctl->tris, (unsigned long long)tc.tris);
+    atomicAdd(&ctl->mesh_rays, (unsigned long long)tc.mesh_rays);
+  }
+}
+
+__global__ void __launch_bounds__(kBlock, kSegPerSM) k_extend_post(Ctl *ctl, DScene sc, ExtendOut out, TaskQ tq, int round, float t_min,
+                                                                   float t_max) {
+  __shared__ uint32_t s_ntask;
+  const uint32_t seg = blockIdx.x, tid = threadIdx.x;
+  const uint32_t n = tq.cnt[(uint32_t)round * gridDim.x + seg], seg_base = seg * out.b.cap;
+  const int par = round & 1;
+  if (tid == 0) s_ntask = 0;
+  __syncthreads();
+  for (uint32_t c0 = 0; c0 < n; c0 += (uint32_t)kBlock) {
+    const uint32_t j = seg_base + c0 + tid;
+    int park = -1;
+    MeshRay mr;
+    float closest = t_max;
+    uint32_t i = 0;
+    if (c0 + tid < n) {
+      const uint2 rk = tq.ray[par][j];
+      const float2 res = tq.res[par][j];
+      i = rk.x;
+      const int k = (int)rk.y;
+      const float4 o4 = out.b.ray_o[i], d4 = out.b.ray_d[i];
+      const Ray ray{v3(o4.x, o4.y, o4.z), v3(d4.x, d4.y, d4.z)};
+      const bool any = (f2u(out.b.hit1[i].w) & kHitBit) != 0u;
+      if (any) closest = out.b.hit0[i].w;  // == the t_max the traversal ran with
+      Hit best;
+      best.triangle = -1;
+      bool improved = false;
+      const uint32_t tri = f2u(res.y);
+      if (tri != 0xffffffffu) {
+        const DObject *ob = sc.objects + k;
+        const MeshRay omr = mesh_object_ray(ob->f, ray);  // same inputs, same bits as in k_extend_pre
+        MeshHit mh;
+        mh.t = res.x, mh.tri = tri, mh.order = 0u;
+        Hit tmp;
+        if (mesh_finish(ob->f, sc.meshes[ob->mesh], ray, omr, mh, t_min, closest, tmp)) {
+          improved = true;
+          closest = tmp.t;
+          best = tmp;
+          best.object = k;
+          best.material = ob->material;
+        }
+      }
+      park = scan_objects(sc, ray, t_min, closest, best, improved, k + 1, mr);
+      if (improved) write_hit(out, i, best);  // otherwise the record parked by the previous stage stands
+    }
+    park_tasks(&s_ntask, tq, par ^ 1, seg_base, park, i, mr, closest);
+  }
+  __syncthreads();
+  if (tid == 0) tq.cnt[(uint32_t)(round + 1) * gridDim.x + seg] = s_ntask;
+}
+
+// ---- sm_100a asynchronous bulk copy (TMA, 1-D) + mbarrier, raw PTX ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// global -> shared, completion (byte count) signalled on the mbarrier; SASS: UBLKCP
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+constexpr int kShadeClasses = 10;  // 0 = miss, 1 + material type (8 types), 9 = no ray (tail of the last chunk)
+constexpr int kShadeArrays = 5;    // ray_o, ray_d, beta, hit0, hit1
+constexpr size_t kShadeSmem = 2 * kShadeArrays * kBlock * sizeof(float4) + 128;  // two staged chunks + alignment slack
+
+// Block-wide exclusive offsets for a per-thread flag: ranks from the warp ballot, warp totals through shared memory.
+// Returns this thread's offset (valid if `flag`); *total = number of flagged threads.  Two block barriers.
+__device__ __forceinline__ uint32_t block_rank(bool flag, uint32_t *s_warp /* [kBlock/32 + 1] */, uint32_t *total) {
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t mask = __ballot_sync(0xffffffffu, flag);
+  if (lane == 0) s_warp[warp] = (uint32_t)__popc(mask);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t tot = 0;
+    for (int w = 0; w < kBlock / 32; w++) {
+      const uint32_t c = s_warp[w];
+      s_warp[w] = tot;
+      tot += c;
+    }
+    s_warp[kBlock / 32] = tot;
+  }
+  __syncthreads();
+  *total = s_warp[kBlock / 32];
+  return s_warp[warp] + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+}
+
+// shade (+ regenerate): emitted + scatter (renderer.rs:26-36) or sky (renderer.rs:38-63) for every ray of the segment,
+// survivors written back in place; then fresh camera paths (renderer.rs:96-99, camera.rs:33-42) fill the free slots.
+//
+// Rays arrive in no particular order, so a warp would see a mix of misses and of every material and run all of their
+// code (measured: 11.5 of 32 lanes active), and waiting for one's own loads leaves the kernel latency-bound.  Hence a
+// two-stage pipeline over 256-ray chunks:
+//   * one thread issues five 1-D bulk async copies (TMA; ray_o, ray_d, beta, hit0, hit1 slices, 4 KB each) of the NEXT
+//     chunk into shared memory, completion counted on an mbarrier, while the block shades the current one;
+//   * the current chunk is counting-sorted by (miss | material type) in shared memory; thread t shades the t-th ray of
+//     that order straight out of the staged copy, so warps are homogeneous except at class boundaries;
+//   * survivors go to the front of the segment (block-local cursor; always behind the chunk being read, and the chunk
+//     itself is already staged, so in place is safe).
+__global__ void __launch_bounds__(kBlock, kSegPerSM) k_shade(Ctl *ctl, DScene sc, RenderParams rp, Buffers b, float *accum) {
+  extern __shared__ uint8_t s_dyn[];
+  float4 *s_raw = reinterpret_cast<float4 *>((reinterpret_cast<uintptr_t>(s_dyn) + 127) & ~(uintptr_t)127);  // [2][5][256]
+  __shared__ uint16_t s_perm[kBlock];
+  __shared__ uint32_t s_cnt[kBlock / 32][kShadeClasses];
+  __shared__ uint32_t s_off[kBlock / 32][kShadeClasses];
+  __shared__ uint32_t s_warp[kBlock / 32 + 1];
+  __shared__ unsigned long long s_first;
+  __shared__ uint32_t s_avail;
+  __shared__ __align__(8) uint64_t s_bar[2];
+  const uint32_t seg = blockIdx.x;
+  const uint32_t n = b.cnt[seg], seg_base = seg * b.cap;
+  const uint32_t n_chunks = (n + (uint32_t)kBlock - 1) / (uint32_t)kBlock;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const float4 *g_arr[kShadeArrays] = {b.ray_o + seg_base, b.ray_d + seg_base, b.beta + seg_base, b.hit0 + seg_base, b.hit1 + seg_base};
+
+  auto issue = [&](uint32_t chunk, uint32_t buf) {  // one thread
+    const uint32_t first = chunk * (uint32_t)kBlock;
+    const uint32_t cnt = n - first < (uint32_t)kBlock ? n - first : (uint32_t)kBlock;
+    const uint32_t bytes = cnt * (uint32_t)sizeof(float4);
+    mbar_expect_tx(&s_bar[buf], bytes * kShadeArrays);
+#pragma unroll
+    for (int a = 0; a < kShadeArrays; a++)
+      bulk_g2s(s_raw + ((size_t)buf * kShadeArrays + a) * kBlock, g_arr[a] + first, bytes, &s_bar[buf]);
+  };
+
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0 && n_chunks > 0) issue(0, 0);
+
+  uint32_t w = 0;  // survivors written so far = write cursor inside the segment (same value in every thread)
+  for (uint32_t chunk = 0; chunk < n_chunks; chunk++) {
+    const uint32_t buf = chunk & 1u;
+    // the other stage was last read in the previous iteration, which ended with a block barrier
+    if (tid == 0 && chunk + 1 < n_chunks) issue(chunk + 1, buf ^ 1u);
+    const uint32_t first = chunk * (uint32_t)kBlock;
+    const uint32_t in_chunk = n - first < (uint32_t)kBlock ? n - first : (uint32_t)kBlock;
+    const float4 *raw = s_raw + (size_t)buf * kShadeArrays * kBlock;
+    mbar_wait(&s_bar[buf], (chunk >> 1) & 1u);
+
+    uint32_t key = kShadeClasses - 1;
+    if (tid < in_chunk) {
+      const uint32_t bits0 = f2u(raw[4 * kBlock + tid].w);
+      key = (bits0 & kHitBit) ? 1u + (uint32_t)sc.materials[bits0 & kMatMask].type : 0u;
+    }
+    uint32_t rank = 0;
+#pragma unroll
+    for (uint32_t c = 0; c < (uint32_t)kShadeClasses; c++) {
+      const uint32_t m = __ballot_sync(0xffffffffu, key == c);
+      if (key == c) rank = (uint32_t)__popc(m & ((1u << lane) - 1u));
+      if (lane == 0) s_cnt[warp][c] = (uint32_t)__popc(m);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t tot = 0;
+      if (lane < (uint32_t)kShadeClasses)
+        for (int ww = 0; ww < kBlock / 32; ww++) tot += s_cnt[ww][lane];
+      uint32_t incl = tot;  // inclusive scan over the classes
+#pragma unroll
+      for (int d = 1; d < 16; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (uint32_t)d) incl += v;
+      }
+      if (lane < (uint32_t)kShadeClasses) {
+        uint32_t off = incl - tot;
+        for (int ww = 0; ww < kBlock / 32; ww++) {
+          s_off[ww][lane] = off;
+          off += s_cnt[ww][lane];
+        }
+      }
+    }
+    __syncthreads();
+    s_perm[s_off[warp][key] + rank] = (uint16_t)tid;
+    __syncthreads();
+
+    bool alive = false;
+    float4 no, nd, nb;
+    if (tid < in_chunk) {  // the "no ray" class sorts last
+      const uint32_t j = s_perm[tid];
+      const float4 o4 = raw[0 * kBlock + j], d4 = raw[1 * kBlock + j], b4 = raw[2 * kBlock + j];
+      const float4 h1 = raw[4 * kBlock + j];
+      const uint32_t pixel = f2u(o4.w), sample = f2u(d4.w), bounce = f2u(b4.w);
+      const uint32_t bits = f2u(h1.w);
+      const V3 beta = v3(b4.x, b4.y, b4.z);
+      const V3 ray_d = v3(d4.x, d4.y, d4.z);
+      V3 radiance = v3(0, 0, 0);
+      bool add = false;
+      if (!(bits & kHitBit)) {
+        radiance = beta * sky_color(sc, ray_d);
+        add = true;
+      } else {
+        const float4 h0 = raw[3 * kBlock + j];
+        const DMaterial m = sc.materials[bits & kMatMask];
+        const V3 e = mat_emitted(m);
+        if (e.x != 0.0f || e.y != 0.0f || e.z != 0.0f) {
+          radiance = beta * e;
+          add = true;
+        }
+        const Uniforms4 u = philox_uniforms(rp.seed, pixel, sample, bounce, 0u);
+        Ray sc_ray;
+        V3 att;
+        if (mat_scatter(m, ray_d, v3(h0.x, h0.y, h0.z), v3(h1.x, h1.y, h1.z), (bits & kFrontBit) != 0u, u.u, sc_ray, att)) {
+          // trace_ray(scattered, depth - 1): depth 0 returns black (renderer.rs:20-22)
+          if (bounce + 1u < (uint32_t)rp.max_depth) {
+            alive = true;
+            const V3 nbeta = beta * att;
+            no = make_float4(sc_ray.o.x, sc_ray.o.y, sc_ray.o.z, o4.w);
+            nd = make_float4(sc_ray.d.x, sc_ray.d.y, sc_ray.d.z, d4.w);
+            nb = make_float4(nbeta.x, nbeta.y, nbeta.z, u2f(bounce + 1u));
+          }
+        }
+      }
+      if (add) {
+        float *px = accum + (size_t)pixel * 3;
+        atomicAdd(px + 0, radiance.x);
+        atomicAdd(px + 1, radiance.y);
+        atomicAdd(px + 2, radiance.z);
+      }
+    }
+    uint32_t total;
+    const uint32_t off = block_rank(alive, s_warp, &total);  // two barriers: stage `buf`, s_perm, s_cnt, s_off are free after it
+    if (alive) {
+      const uint32_t slot = seg_base + w + off;
+      b.ray_o[slot] = no;
+      b.ray_d[slot] = nd;
+      b.beta[slot] = nb;
+    }
+    w += total;
+    __syncthreads();  // s_warp is reused by the next block_rank
+  }
+
+  // ---- regeneration: top the segment up with fresh camera paths.  Path index -> (sample, 32-pixel row of one of this
+  // rank's 32x32 tiles, lane): a warp starts 32 horizontally adjacent pixels of one sample (coherent primary rays,
+  // distinct film addresses), but consecutive rows are scattered over the image by a multiplicative bijection, so every
+  // segment holds a uniform sample of the frame — segments are statically owned by blocks, and a segment that got all
+  // the rays of the mesh's screen region would make its block the straggler of every traversal pass.  Pixels of partial
+  // border tiles that fall outside the image start no path.
+  if (tid == 0) {
+    const uint32_t free_slots = b.cap - w;
+    unsigned long long first = ctl->total_paths;
+    if (free_slots > 0 && ctl->next_path < ctl->total_paths) first = atomicAdd(&ctl->next_path, (unsigned long long)free_slots);
+    s_first = first;
+    s_avail = first < ctl->total_paths ? (uint32_t)min((unsigned long long)free_slots, ctl->total_paths - first) : 0u;
+  }
+  __syncthreads();
+  const unsigned long long first_path = s_first;
+  const uint32_t avail = s_avail;
+  const unsigned long long per_sample = (unsigned long long)rp.n_my_tiles * 1024ull;
+  for (uint32_t j0 = 0; j0 < avail; j0 += (uint32_t)kBlock) {
+    const uint32_t j = j0 + tid;
+    bool valid = j < avail;
+    uint32_t pixel = 0, sample = 0;
+    int x = 0, y = 0;
+    if (valid) {
+      const unsigned long long p = first_path + j;
+      const uint32_t s = (uint32_t)(p / per_sample);
+      const uint32_t r0 = (uint32_t)(p - (unsigned long long)s * per_sample);
+      const uint32_t row = (uint32_t)(((unsigned long long)(r0 >> 5) * rp.row_mult) % (unsigned long long)(per_sample >> 5));
+      const uint32_t r = (row << 5) | (r0 & 31u);
+      const uint32_t local_tile = r >> 10, in_tile = r & 1023u;
+      const uint32_t tile = local_tile * (uint32_t)rp.tile_mod + (uint32_t)rp.tile_rem;
+      x = (int)((tile % (uint32_t)rp.tiles_x) * 32u + (in_tile & 31u));
+      y = (int)((tile / (uint32_t)rp.tiles_x) * 32u + (in_tile >> 5));
+      valid = x < rp.width && y < rp.height;
+      pixel = (uint32_t)(y * rp.width + x);
+      sample = (uint32_t)rp.sample_begin + s;
+    }
+    uint32_t total;
+    const uint32_t off = block_rank(valid, s_warp, &total);
+    if (valid) {
+      const uint32_t slot = seg_base + w + off;
+      const Uniforms4 jit = philox_uniforms(rp.seed, pixel, sample, 0xffffffffu, 0u);
+      const float u = ((float)x + jit.u[0]) / (float)rp.width;   // renderer.rs:96
+      const float v = ((float)y + jit.u[1]) / (float)rp.height;  // renderer.rs:97
+      const Ray ray = camera_get_ray(rp.cam, u, v);
+      b.ray_o[slot] = make_float4(ray.o.x, ray.o.y, ray.o.z, u2f(pixel));
+      b.ray_d[slot] = make_float4(ray.d.x, ray.d.y, ray.d.z, u2f(sample));
+      b.beta[slot] = make_float4(1.0f, 1.0f, 1.0f, u2f(0u));
+    }
+    w += total;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    b.cnt[seg] = w;
+    if (w) atomicAdd(&ctl->n_live, w);
+  }
+}
+
+// out = rgb * scale (renderer.rs:103)
+__global__ void k_scale(const float *in, float *out, size_t n, float scale) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i] * scale;
+}
+// renderer.rs:112-120 + color.rs:87-93
+__global__ void k_resolve(const float *rgb, size_t n_pixels, float scale, uint32_t *out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_pixels) out[i] = resolve_pixel(rgb[i * 3] * scale, rgb[i * 3 + 1] * scale, rgb[i * 3 + 2] * scale);
+}
+
+// ---- parity hooks: the same device functions / kernels, driven by caller-provided inputs ---------------------
+// ptc_intersect runs the very kernels the renderer uses (k_extend_*); these two only repack inputs / outputs.
+__global__ void k_pack_rays(const float *o, const float *d, size_t n, float4 *ro, float4 *rd) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  ro[i] = make_float4(o[i * 3], o[i * 3 + 1], o[i * 3 + 2], 0.0f);
+  rd[i] = make_float4(d[i * 3], d[i * 3 + 1], d[i * 3 + 2], 0.0f);
+}
+__global__ void k_unpack_hits(const float4 *hit0, const float4 *hit1, const int2 *ids, size_t n, ptc_hit *out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  ptc_hit r;
+  memset(&r, 0, sizeof(r));
+  const float4 h1 = hit1[i];
+  const uint32_t bits = f2u(h1.w);
+  if (bits & kHitBit) {
+    const float4 h0 = hit0[i];
+    const int2 id = ids[i];
+    r.object = id.x, r.triangle = id.y;
+    r.t = h0.w;
+    r.position[0] = h0.x, r.position[1] = h0.y, r.position[2] = h0.z;
+    r.normal[0] = h1.x, r.normal[1] = h1.y, r.normal[2] = h1.z;
+    r.front_face = (bits & kFrontBit) ? 1 : 0;
+    r.material = (int32_t)(bits & kMatMask);
+  } else {
+    r.object = -1, r.triangle = -1, r.material = -1;
+  }
+  out[i] = r;
+}
+
+__global__ void k_primary_rays(RenderParams rp, uint32_t sample, float *out_o, float *out_d) {
+  const uint32_t pixel = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pixel >= (uint32_t)(rp.width * rp.height)) return;
+  const int x = (int)(pixel % (uint32_t)rp.width), y = (int)(pixel / (uint32_t)rp.width);
+  const Uniforms4 jit = philox_uniforms(rp.seed, pixel, sample, 0xffffffffu, 0u);
+  const float u = ((float)x + jit.u[0]) / (float)rp.width;
+  const float v = ((float)y + jit.u[1]) / (float)rp.height;
+  const Ray ray = camera_get_ray(rp.cam, u, v);
+  out_o[pixel * 3 + 0] = ray.o.x, out_o[pixel * 3 + 1] = ray.o.y, out_o[pixel * 3 + 2] = ray.o.z;
+  out_d[pixel * 3 + 0] = ray.d.x, out_d[pixel * 3 + 1] = ray.d.y, out_d[pixel * 3 + 2] = ray.d.z;
+}
+
+__global__ void k_scatter(DMaterial m, const float *dirs, const float *pos, const float *nrm, const int32_t *front,
+                          const float *u4, size_t n, int32_t *scattered, float *out_o, float *out_d, float *att_out,
+                          float *emitted) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Ray sr{v3(0, 0, 0), v3(0, 0, 0)};
+  V3 att = v3(0, 0, 0);
+  const V3 e = mat_emitted(m);
+  const float u[4] = {u4[i * 4], u4[i * 4 + 1], u4[i * 4 + 2], u4[i * 4 + 3]};
+  const bool ok = mat_scatter(m, v3(dirs[i * 3], dirs[i * 3 + 1], dirs[i * 3 + 2]), v3(pos[i * 3], pos[i * 3 + 1], pos[i * 3 + 2]),
+                              v3(nrm[i * 3], nrm[i * 3 + 1], nrm[i * 3 + 2]), front[i] != 0, u, sr, att);
+  scattered[i] = ok ? 1 : 0;
+  out_o[i * 3] = sr.o.x, out_o[i * 3 + 1] = sr.o.y, out_o[i * 3 + 2] = sr.o.z;
+  out_d[i * 3] = sr.d.x, out_d[i * 3 + 1] = sr.d.y, out_d[i * 3 + 2] = sr.d.z;
+  att_out[i * 3] = att.x, att_out[i * 3 + 1] = att.y, att_out[i * 3 + 2] = att.z;
+  emitted[i * 3] = e.x, emitted[i * 3 + 1] = e.y, emitted[i * 3 + 2] = e.z;
+}
+
+__global__ void k_philox(U4 c, uint32_t k0, uint32_t k1, uint32_t *out) {
+  const U4 r = philox4x32_10(c, k0, k1);
+  out[0] = r.x, out[1] = r.y, out[2] = r.z, out[3] = r.w;
+}
+
+// segment counts for a flat array of n rays laid out at slots [0, n): segment b holds min(cap, n - b * cap)
+__global__ void k_fill_counts(uint32_t *cnt, uint32_t n_seg, uint32_t cap, uint32_t n) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_seg) return;
+  const unsigned long long lo = (unsigned long long)b * cap;
+  cnt[b] = lo >= n ? 0u : (uint32_t)min((unsigned long long)cap, (unsigned long long)n - lo);
+}
+
+}  // namespace ptw
