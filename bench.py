@@ -302,8 +302,11 @@ def main():
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "kernel_share": {"extend": ext_ms / render_ms, "shade": shade_ms / render_ms,
-                             "other (generate, advance, gaps)": 1.0 - (ext_ms + shade_ms) / render_ms},
+            "kernel_share": {"k_extend_pre": sum(s.pre_ms for s in stats) / render_ms,
+                             "k_traverse": sum(s.traverse_ms for s in stats) / render_ms,
+                             "k_extend_post": sum(s.post_ms for s in stats) / render_ms,
+                             "k_shade (incl. path regeneration)": shade_ms / render_ms,
+                             "launch gaps": max(0.0, 1.0 - (ext_ms + shade_ms) / render_ms)},
             "roofline": {"kernel": "extend stage = k_extend_pre + k_traverse + k_extend_post (one logical kernel, timed together)", "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": peak_kind,
                          "algorithmic_bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray,

@@ -59,6 +59,7 @@ struct TravState {
   uint32_t octinv;
   uint2 ng;  // node group: x = first child index, y = hit bits [24,32) | imask
   uint2 tg;  // triangle group: x = first triangle, y = hit bits [0,24)
+  uint2 tg2; // second triangle group, filled by a node step taken while `tg` still has triangles pending (tg2 != 0 => tg != 0)
 };
 
 PT_HD void trav_begin(TravState &s, V3 o, V3 d, float t_min, float t_max) {
@@ -73,12 +74,14 @@ PT_HD void trav_begin(TravState &s, V3 o, V3 d, float t_min, float t_max) {
   s.octinv = 7u - (sx | (sy << 1) | (sz << 2));
   s.ng = make_uint2(0u, 0x80000000u);
   s.tg = make_uint2(0u, 0u);
+  s.tg2 = make_uint2(0u, 0u);
 }
 PT_HD bool trav_has_node(const TravState &s) { return s.ng.y > 0x00FFFFFFu; }
 PT_HD bool trav_has_tri(const TravState &s) { return s.tg.y != 0u; }
 
 // Pops the nearest pending child of the node group, pushes the rest, tests the child's 8 boxes.
-// Precondition: trav_has_node(s) && !trav_has_tri(s).
+// Precondition: trav_has_node(s) && s.tg2.y == 0 (the new leaf hits go to `tg`, or to `tg2` while `tg` is still busy, so
+// a lane can walk on to its next node while it works through the triangles of the previous one).
 template <bool COUNT>
 PT_HD void trav_node(const DMesh &m, TravState &s, uint2 *stack, int &sp, TraversalCounters *ctr) {
   const uint32_t hits = s.ng.y, imask = hits & 0xffu;
@@ -135,16 +138,21 @@ PT_HD void trav_node(const DMesh &m, TravState &s, uint2 *stack, int &sp, Traver
   }
   s.ng.x = f2u(q1.x);
   s.ng.y = (hitmask & 0xFF000000u) | (e >> 24);
-  s.tg.x = f2u(q1.y);
-  s.tg.y = hitmask & 0x00FFFFFFu;
+  const uint2 leaf_hits = make_uint2(f2u(q1.y), hitmask & 0x00FFFFFFu);
+  if (s.tg.y == 0u) s.tg = leaf_hits;
+  else s.tg2 = leaf_hits;
 }
 
 // Tests ONE pending triangle of the triangle group.  Precondition: trav_has_tri(s).
 template <bool COUNT>
 PT_HD void trav_tri(const DMesh &m, TravState &s, TraversalCounters *ctr) {
   const int bit = 31 - clz32(s.tg.y);
-  s.tg.y &= ~(1u << bit);
   const float4 *tp = m.tris + (size_t)(s.tg.x + (uint32_t)bit) * 3;
+  s.tg.y &= ~(1u << bit);
+  if (s.tg.y == 0u) {
+    s.tg = s.tg2;
+    s.tg2 = make_uint2(0u, 0u);
+  }
   const float4 t0 = ldg4(tp), t1 = ldg4(tp + 1), t2 = ldg4(tp + 2);
   if (COUNT) ctr->tris++;
   // bvh.rs:94-116, same operation order, no fusing

@@ -227,15 +227,16 @@ __global__ void __launch_bounds__(kBlock, kSegPerSM) k_traverse(Ctl *ctl, DScene
       continue;
     }
     if (active) {
-      if (!trav_has_tri(s) && !trav_has_node(s)) {
+      // one node step AND one triangle test per turn: the node step does not wait for the lane's pending triangles
+      if (!trav_has_node(s)) {
         if (sp > 0) {
           s.ng = stack[--sp];
-        } else {
+        } else if (!trav_has_tri(s)) {
           tq.res[par][task] = make_float2(s.best_t, u2f(s.best_tri));
           active = false;
         }
       }
-      if (active && !trav_has_tri(s) && trav_has_node(s)) trav_node<COUNT>(mesh, s, stack, sp, &tc);
+      if (active && trav_has_node(s) && s.tg2.y == 0u) trav_node<COUNT>(mesh, s, stack, sp, &tc);
       if (active && trav_has_tri(s)) trav_tri<COUNT>(mesh, s, &tc);
     }
   }
