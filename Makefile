@@ -7,7 +7,7 @@ NVCC ?= nvcc
 CXX ?= g++
 PKG := raytracer-rust_b200
 CSRC := $(PKG)/csrc
-HDRS := $(wildcard $(CSRC)/*.h) include/ptcore.h include/pthost.h
+HDRS := $(wildcard $(CSRC)/*.h) $(wildcard $(CSRC)/*.cuh) include/ptcore.h include/pthost.h
 
 # --fmad=false / -ffp-contract=off: the reference (rustc, no target-cpu flags) never fuses a*b+c, and closest-hit
 # parity is judged bit-exact, so neither do we; conservative box tests ask for fmaf() explicitly.

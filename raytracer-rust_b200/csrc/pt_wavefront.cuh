@@ -42,8 +42,17 @@ struct Ctl {
   unsigned long long total_paths;  // path index space of this call (padded tiles x samples)
   unsigned long long rays;         // extend items so far = trace_ray calls with depth > 0
   unsigned long long nodes, tris, mesh_rays;  // PTC_FLAG_COUNTERS
-  uint32_t n_live;      // rays alive after the last shade (sum of the segment counts)
-  uint32_t iterations;
+  uint32_t n_live[2];      // rays alive after the last shade (sum of the segment counts), per half-wavefront
+  uint32_t iterations[2];  // per half-wavefront
+};
+
+// The segments are split into two halves that run the same sequence of stage kernels on two streams, half an iteration
+// apart in practice: while one half is in its (ALU-bound, ragged-tailed) traversal the other is in its (latency-bound)
+// shading, so the tails of one fill with the other's work.  A kernel launch covers segments [seg0, seg0 + gridDim.x).
+struct SegRange {
+  uint32_t seg0;   // first segment of this launch
+  uint32_t n_seg;  // segments of the whole pool (stride of the task-count table)
+  uint32_t half;   // 0 / 1
 };
 
 struct RenderParams {
@@ -143,19 +152,15 @@ __device__ __forceinline__ void park_tasks(uint32_t *s_ntask, const TaskQ &tq, i
   }
 }
 
-__global__ void __launch_bounds__(kBlock, kSegPerSM) k_extend_pre(Ctl *ctl, DScene sc, ExtendOut out, TaskQ tq, float t_min, float t_max) {
+// ---- the four stages, each written for ONE block working on ITS segment.  They are called either from the per-stage
+// kernels below (PTC_FLAG_TIMING / PTC_FLAG_COUNTERS / ptc_intersect: one launch per stage, CUDA events in between) or
+// back to back from the persistent kernel k_wavefront.
+__device__ __forceinline__ void stage_pre(uint32_t seg, uint32_t n_seg, const DScene &sc, const ExtendOut &out, const TaskQ &tq,
+                                          float t_min, float t_max) {
   __shared__ uint32_t s_ntask;
-  const uint32_t seg = blockIdx.x, tid = threadIdx.x;
+  const uint32_t tid = threadIdx.x;
   const uint32_t n = out.b.cnt[seg], seg_base = seg * out.b.cap;
-  if (tid == 0) {
-    s_ntask = 0;
-    if (seg == 0) {  // iteration bookkeeping (the previous shade has finished: kernels of a stream run in order)
-      const uint32_t live = ctl->n_live;
-      ctl->rays += live;
-      if (live) ctl->iterations++;
-      ctl->n_live = 0;
-    }
-  }
+  if (tid == 0) s_ntask = 0;
   __syncthreads();
   for (uint32_t c0 = 0; c0 < n; c0 += (uint32_t)kBlock) {
     const uint32_t i = seg_base + c0 + tid;
@@ -175,14 +180,14 @@ __global__ void __launch_bounds__(kBlock, kSegPerSM) k_extend_pre(Ctl *ctl, DSce
   }
   __syncthreads();
   if (tid == 0 && tq.cnt) tq.cnt[seg] = s_ntask;
+  (void)n_seg;
 }
 
 template <bool COUNT>
-__global__ void __launch_bounds__(kBlock, kSegPerSM) k_traverse(Ctl *ctl, DScene sc, TaskQ tq, int round, float t_min, uint32_t cap,
-                                                                uint32_t refill_lanes) {
+__device__ __forceinline__ void stage_traverse(uint32_t seg, uint32_t n_seg, Ctl *ctl, const DScene &sc, const TaskQ &tq, int round,
+                                               float t_min, uint32_t cap, uint32_t refill_lanes) {
   __shared__ uint32_t s_cur;
-  const uint32_t seg = blockIdx.x;
-  const uint32_t n = tq.cnt[(uint32_t)round * gridDim.x + seg], seg_base = seg * cap;
+  const uint32_t n = tq.cnt[(uint32_t)round * n_seg + seg], seg_base = seg * cap;
   const int par = round & 1;
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t lt_mask = (1u << lane) - 1u;
@@ -247,11 +252,11 @@ __global__ void __launch_bounds__(kBlock, kSegPerSM) k_traverse(Ctl *ctl, DScene
   }
 }
 
-__global__ void __launch_bounds__(kBlock, kSegPerSM) k_extend_post(Ctl *ctl, DScene sc, ExtendOut out, TaskQ tq, int round, float t_min,
-                                                                   float t_max) {
+__device__ __forceinline__ void stage_post(uint32_t seg, uint32_t n_seg, const DScene &sc, const ExtendOut &out, const TaskQ &tq,
+                                           int round, float t_min, float t_max) {
   __shared__ uint32_t s_ntask;
-  const uint32_t seg = blockIdx.x, tid = threadIdx.x;
-  const uint32_t n = tq.cnt[(uint32_t)round * gridDim.x + seg], seg_base = seg * out.b.cap;
+  const uint32_t tid = threadIdx.x;
+  const uint32_t n = tq.cnt[(uint32_t)round * n_seg + seg], seg_base = seg * out.b.cap;
   const int par = round & 1;
   if (tid == 0) s_ntask = 0;
   __syncthreads();
@@ -294,7 +299,7 @@ __global__ void __launch_bounds__(kBlock, kSegPerSM) k_extend_post(Ctl *ctl, DSc
     park_tasks(&s_ntask, tq, par ^ 1, seg_base, park, i, mr, closest);
   }
   __syncthreads();
-  if (tid == 0) tq.cnt[(uint32_t)(round + 1) * gridDim.x + seg] = s_ntask;
+  if (tid == 0) tq.cnt[(uint32_t)(round + 1) * n_seg + seg] = s_ntask;
 }
 
 // ---- sm_100a asynchronous bulk copy (TMA, 1-D) + mbarrier, raw PTX ----
@@ -359,17 +364,17 @@ __device__ __forceinline__ uint32_t block_rank(bool flag, uint32_t *s_warp /* [k
 //     that order straight out of the staged copy, so warps are homogeneous except at class boundaries;
 //   * survivors go to the front of the segment (block-local cursor; always behind the chunk being read, and the chunk
 //     itself is already staged, so in place is safe).
-__global__ void __launch_bounds__(kBlock, kSegPerSM) k_shade(Ctl *ctl, DScene sc, RenderParams rp, Buffers b, float *accum) {
-  extern __shared__ uint8_t s_dyn[];
-  float4 *s_raw = reinterpret_cast<float4 *>((reinterpret_cast<uintptr_t>(s_dyn) + 127) & ~(uintptr_t)127);  // [2][5][256]
+// `s_raw` = the two staged chunks [2][5][256] float4 (dynamic shared memory), `s_bar` = their two mbarriers (initialised
+// by the calling kernel), `used[b]` = how many times stage b has been waited on so far (its mbarrier phase parity).
+// Returns the new ray count of the segment.
+__device__ __forceinline__ uint32_t stage_shade(uint32_t seg, uint32_t half, Ctl *ctl, const DScene &sc, const RenderParams &rp, const Buffers &b,
+                                                float *accum, float4 *s_raw, uint64_t *s_bar, uint32_t (&used)[2]) {
   __shared__ uint16_t s_perm[kBlock];
   __shared__ uint32_t s_cnt[kBlock / 32][kShadeClasses];
   __shared__ uint32_t s_off[kBlock / 32][kShadeClasses];
   __shared__ uint32_t s_warp[kBlock / 32 + 1];
   __shared__ unsigned long long s_first;
-  __shared__ uint32_t s_avail;
-  __shared__ __align__(8) uint64_t s_bar[2];
-  const uint32_t seg = blockIdx.x;
+  __shared__ uint32_t s_avail, s_more;
   const uint32_t n = b.cnt[seg], seg_base = seg * b.cap;
   const uint32_t n_chunks = (n + (uint32_t)kBlock - 1) / (uint32_t)kBlock;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -385,11 +390,9 @@ __global__ void __launch_bounds__(kBlock, kSegPerSM) k_shade(Ctl *ctl, DScene sc
       bulk_g2s(s_raw + ((size_t)buf * kShadeArrays + a) * kBlock, g_arr[a] + first, bytes, &s_bar[buf]);
   };
 
-  if (tid == 0) {
-    mbar_init(&s_bar[0], 1);
-    mbar_init(&s_bar[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
+  // hit records written with ordinary stores by the extend stages of this same kernel must be visible to the bulk copy
+  // engine (async proxy)
+  asm volatile("fence.proxy.async;" ::: "memory");
   __syncthreads();
   if (tid == 0 && n_chunks > 0) issue(0, 0);
 
@@ -401,7 +404,8 @@ __global__ void __launch_bounds__(kBlock, kSegPerSM) k_shade(Ctl *ctl, DScene sc
     const uint32_t first = chunk * (uint32_t)kBlock;
     const uint32_t in_chunk = n - first < (uint32_t)kBlock ? n - first : (uint32_t)kBlock;
     const float4 *raw = s_raw + (size_t)buf * kShadeArrays * kBlock;
-    mbar_wait(&s_bar[buf], (chunk >> 1) & 1u);
+    mbar_wait(&s_bar[buf], used[buf] & 1u);
+    used[buf]++;
 
     uint32_t key = kShadeClasses - 1;
     if (tid < in_chunk) {
@@ -500,54 +504,138 @@ __global__ void __launch_bounds__(kBlock, kSegPerSM) k_shade(Ctl *ctl, DScene sc
   // segment holds a uniform sample of the frame — segments are statically owned by blocks, and a segment that got all
   // the rays of the mesh's screen region would make its block the straggler of every traversal pass.  Pixels of partial
   // border tiles that fall outside the image start no path.
-  if (tid == 0) {
-    const uint32_t free_slots = b.cap - w;
-    unsigned long long first = ctl->total_paths;
-    if (free_slots > 0 && ctl->next_path < ctl->total_paths) first = atomicAdd(&ctl->next_path, (unsigned long long)free_slots);
-    s_first = first;
-    s_avail = first < ctl->total_paths ? (uint32_t)min((unsigned long long)free_slots, ctl->total_paths - first) : 0u;
-  }
-  __syncthreads();
-  const unsigned long long first_path = s_first;
-  const uint32_t avail = s_avail;
   const unsigned long long per_sample = (unsigned long long)rp.n_my_tiles * 1024ull;
-  for (uint32_t j0 = 0; j0 < avail; j0 += (uint32_t)kBlock) {
-    const uint32_t j = j0 + tid;
-    bool valid = j < avail;
-    uint32_t pixel = 0, sample = 0;
-    int x = 0, y = 0;
-    if (valid) {
-      const unsigned long long p = first_path + j;
-      const uint32_t s = (uint32_t)(p / per_sample);
-      const uint32_t r0 = (uint32_t)(p - (unsigned long long)s * per_sample);
-      const uint32_t row = (uint32_t)(((unsigned long long)(r0 >> 5) * rp.row_mult) % (unsigned long long)(per_sample >> 5));
-      const uint32_t r = (row << 5) | (r0 & 31u);
-      const uint32_t local_tile = r >> 10, in_tile = r & 1023u;
-      const uint32_t tile = local_tile * (uint32_t)rp.tile_mod + (uint32_t)rp.tile_rem;
-      x = (int)((tile % (uint32_t)rp.tiles_x) * 32u + (in_tile & 31u));
-      y = (int)((tile / (uint32_t)rp.tiles_x) * 32u + (in_tile >> 5));
-      valid = x < rp.width && y < rp.height;
-      pixel = (uint32_t)(y * rp.width + x);
-      sample = (uint32_t)rp.sample_begin + s;
+  for (;;) {
+    if (tid == 0) {
+      const uint32_t free_slots = b.cap - w;
+      const unsigned long long total = ctl->total_paths;
+      unsigned long long first = total;
+      if (free_slots > 0 && ctl->next_path < total) first = atomicAdd(&ctl->next_path, (unsigned long long)free_slots);
+      s_first = first;
+      s_avail = first < total ? (uint32_t)min((unsigned long long)free_slots, total - first) : 0u;
+      s_more = (first + free_slots < total) ? 1u : 0u;  // the supply is not exhausted yet
     }
-    uint32_t total;
-    const uint32_t off = block_rank(valid, s_warp, &total);
-    if (valid) {
-      const uint32_t slot = seg_base + w + off;
-      const Uniforms4 jit = philox_uniforms(rp.seed, pixel, sample, 0xffffffffu, 0u);
-      const float u = ((float)x + jit.u[0]) / (float)rp.width;   // renderer.rs:96
-      const float v = ((float)y + jit.u[1]) / (float)rp.height;  // renderer.rs:97
-      const Ray ray = camera_get_ray(rp.cam, u, v);
-      b.ray_o[slot] = make_float4(ray.o.x, ray.o.y, ray.o.z, u2f(pixel));
-      b.ray_d[slot] = make_float4(ray.d.x, ray.d.y, ray.d.z, u2f(sample));
-      b.beta[slot] = make_float4(1.0f, 1.0f, 1.0f, u2f(0u));
-    }
-    w += total;
     __syncthreads();
+    const unsigned long long first_path = s_first;
+    const uint32_t avail = s_avail;
+    for (uint32_t j0 = 0; j0 < avail; j0 += (uint32_t)kBlock) {
+      const uint32_t j = j0 + tid;
+      bool valid = j < avail;
+      uint32_t pixel = 0, sample = 0;
+      int x = 0, y = 0;
+      if (valid) {
+        const unsigned long long p = first_path + j;
+        const uint32_t s = (uint32_t)(p / per_sample);
+        const uint32_t r0 = (uint32_t)(p - (unsigned long long)s * per_sample);
+        const uint32_t row = (uint32_t)(((unsigned long long)(r0 >> 5) * rp.row_mult) % (unsigned long long)(per_sample >> 5));
+        const uint32_t r = (row << 5) | (r0 & 31u);
+        const uint32_t local_tile = r >> 10, in_tile = r & 1023u;
+        const uint32_t tile = local_tile * (uint32_t)rp.tile_mod + (uint32_t)rp.tile_rem;
+        x = (int)((tile % (uint32_t)rp.tiles_x) * 32u + (in_tile & 31u));
+        y = (int)((tile / (uint32_t)rp.tiles_x) * 32u + (in_tile >> 5));
+        valid = x < rp.width && y < rp.height;
+        pixel = (uint32_t)(y * rp.width + x);
+        sample = (uint32_t)rp.sample_begin + s;
+      }
+      uint32_t total;
+      const uint32_t off = block_rank(valid, s_warp, &total);
+      if (valid) {
+        const uint32_t slot = seg_base + w + off;
+        const Uniforms4 jit = philox_uniforms(rp.seed, pixel, sample, 0xffffffffu, 0u);
+        const float u = ((float)x + jit.u[0]) / (float)rp.width;   // renderer.rs:96
+        const float v = ((float)y + jit.u[1]) / (float)rp.height;  // renderer.rs:97
+        const Ray ray = camera_get_ray(rp.cam, u, v);
+        b.ray_o[slot] = make_float4(ray.o.x, ray.o.y, ray.o.z, u2f(pixel));
+        b.ray_d[slot] = make_float4(ray.d.x, ray.d.y, ray.d.z, u2f(sample));
+        b.beta[slot] = make_float4(1.0f, 1.0f, 1.0f, u2f(0u));
+      }
+      w += total;
+      __syncthreads();
+    }
+    // a batch that fell entirely on out-of-image pixels of border tiles must not look like "no paths left"
+    const bool again = (w == 0u) && (s_more != 0u);
+    __syncthreads();
+    if (!again) break;
   }
   if (tid == 0) {
     b.cnt[seg] = w;
-    if (w) atomicAdd(&ctl->n_live, w);
+    if (w) atomicAdd(&ctl->n_live[half], w);
+  }
+  return w;
+}
+
+// ---- per-stage kernels: one block per segment --------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock, kSegPerSM) k_extend_pre(Ctl *ctl, SegRange sr, DScene sc, ExtendOut out, TaskQ tq, float t_min,
+                                                                  float t_max) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {  // iteration bookkeeping (this half's previous shade has finished: stream order)
+    const uint32_t live = ctl->n_live[sr.half];
+    if (live) {
+      atomicAdd(&ctl->rays, (unsigned long long)live);
+      ctl->iterations[sr.half]++;
+    }
+    ctl->n_live[sr.half] = 0;
+  }
+  stage_pre(sr.seg0 + blockIdx.x, sr.n_seg, sc, out, tq, t_min, t_max);
+}
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlock, kSegPerSM) k_traverse(Ctl *ctl, SegRange sr, DScene sc, TaskQ tq, int round, float t_min,
+                                                                uint32_t cap, uint32_t refill_lanes) {
+  stage_traverse<COUNT>(sr.seg0 + blockIdx.x, sr.n_seg, ctl, sc, tq, round, t_min, cap, refill_lanes);
+}
+__global__ void __launch_bounds__(kBlock, kSegPerSM) k_extend_post(SegRange sr, DScene sc, ExtendOut out, TaskQ tq, int round, float t_min,
+                                                                   float t_max) {
+  stage_post(sr.seg0 + blockIdx.x, sr.n_seg, sc, out, tq, round, t_min, t_max);
+}
+
+__device__ __forceinline__ float4 *shade_smem_setup(uint8_t *s_dyn, uint64_t *s_bar) {
+  if (threadIdx.x == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  return reinterpret_cast<float4 *>((reinterpret_cast<uintptr_t>(s_dyn) + 127) & ~(uintptr_t)127);
+}
+__global__ void __launch_bounds__(kBlock, kSegPerSM) k_shade(Ctl *ctl, SegRange sr, DScene sc, RenderParams rp, Buffers b, float *accum) {
+  extern __shared__ uint8_t s_dyn[];
+  __shared__ __align__(8) uint64_t s_bar[2];
+  float4 *s_raw = shade_smem_setup(s_dyn, s_bar);
+  uint32_t used[2] = {0u, 0u};
+  stage_shade(sr.seg0 + blockIdx.x, sr.half, ctl, sc, rp, b, accum, s_raw, s_bar, used);
+}
+
+// ---- the production path: ONE persistent kernel.  Segments never interact (the only shared state is the path counter
+// and the film), so a block simply loops over the stages of its own segment until the segment is empty and the path
+// supply exhausted: no kernel boundaries, no grid-wide barriers, no host polling, and blocks in different stages overlap
+// on an SM (the ALU-bound traversal of one block fills the issue slots the latency-bound shading of another leaves).
+__global__ void __launch_bounds__(kBlock, kSegPerSM) k_wavefront(Ctl *ctl, DScene sc, RenderParams rp, Buffers b, TaskQ tq, int rounds,
+                                                                 float *accum, uint32_t refill_lanes) {
+  extern __shared__ uint8_t s_dyn[];
+  __shared__ __align__(8) uint64_t s_bar[2];
+  float4 *s_raw = shade_smem_setup(s_dyn, s_bar);
+  const uint32_t seg = blockIdx.x, n_seg = gridDim.x;
+  const ExtendOut out{b, nullptr};
+  uint32_t used[2] = {0u, 0u};
+  unsigned long long my_rays = 0;
+  uint32_t my_iters = 0;
+  uint32_t n = stage_shade(seg, 0u, ctl, sc, rp, b, accum, s_raw, s_bar, used);  // empty segment: pure regeneration
+  while (n > 0) {
+    my_rays += n;
+    my_iters++;
+    __syncthreads();
+    stage_pre(seg, n_seg, sc, out, tq, kEps, INFINITY);  // renderer.rs:24: (EPSILON, +inf)
+    for (int r = 0; r < rounds; r++) {
+      __syncthreads();
+      stage_traverse<false>(seg, n_seg, ctl, sc, tq, r, kEps, b.cap, refill_lanes);
+      __syncthreads();
+      stage_post(seg, n_seg, sc, out, tq, r, kEps, INFINITY);
+    }
+    __syncthreads();
+    n = stage_shade(seg, 0u, ctl, sc, rp, b, accum, s_raw, s_bar, used);
+  }
+  if (threadIdx.x == 0) {
+    atomicAdd(&ctl->rays, my_rays);
+    atomicMax(&ctl->iterations[0], my_iters);
   }
 }
 

@@ -127,6 +127,8 @@ struct ptc_scene {
   static constexpr int kRing = 4;
   cudaEvent_t ring_ev[kRing] = {nullptr, nullptr, nullptr, nullptr};
   cudaStream_t own_stream = nullptr;
+  cudaStream_t aux_stream = nullptr;  // second half-wavefront
+  cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
   std::vector<cudaEvent_t> timing_events;
 
   uint32_t segments() const { return (uint32_t)(sm_count * kSegPerSM); }
@@ -138,6 +140,9 @@ struct ptc_scene {
       if (e) cudaEventDestroy(e);
     for (auto &e : timing_events) cudaEventDestroy(e);
     if (own_stream) cudaStreamDestroy(own_stream);
+    if (aux_stream) cudaStreamDestroy(aux_stream);
+    if (fork_ev) cudaEventDestroy(fork_ev);
+    if (join_ev) cudaEventDestroy(join_ev);
   }
 };
 
@@ -145,22 +150,18 @@ namespace {
 
 enum Stage { ST_PRE = 0, ST_TRAVERSE, ST_POST, ST_SHADE, ST_COUNT };
 
-// One extend pass = pre, then (traverse, post) once per mesh object a ray can meet.  Returns the number of launches.
+// One extend pass over ALL segments on one stream (ptc_intersect) = pre, then (traverse, post) once per mesh object a ray
+// can meet.  Returns the number of launches.
 int launch_extend(cudaStream_t stream, uint32_t segments, int rounds, Ctl *ctl, const DScene &ds, const ExtendOut &eo, const TaskQ &tq,
-                  float t_min, float t_max, bool counters, const std::function<void(int)> *mark = nullptr) {
-  static const uint32_t refill = getenv("PTC_REFILL") ? (uint32_t)atoi(getenv("PTC_REFILL")) : kRefillLanes;  // tuning knob
-  int launches = 1;
-  if (mark) (*mark)(ST_PRE);
-  k_extend_pre<<<segments, kBlock, 0, stream>>>(ctl, ds, eo, tq, t_min, t_max);
+                  float t_min, float t_max, bool counters) {
+  const SegRange sr{0u, segments, 0u};
+  k_extend_pre<<<segments, kBlock, 0, stream>>>(ctl, sr, ds, eo, tq, t_min, t_max);
   for (int r = 0; r < rounds; r++) {
-    if (mark) (*mark)(ST_TRAVERSE);
-    if (counters) k_traverse<true><<<segments, kBlock, 0, stream>>>(ctl, ds, tq, r, t_min, eo.b.cap, refill);
-    else k_traverse<false><<<segments, kBlock, 0, stream>>>(ctl, ds, tq, r, t_min, eo.b.cap, refill);
-    if (mark) (*mark)(ST_POST);
-    k_extend_post<<<segments, kBlock, 0, stream>>>(ctl, ds, eo, tq, r, t_min, t_max);
-    launches += 2;
+    if (counters) k_traverse<true><<<segments, kBlock, 0, stream>>>(ctl, sr, ds, tq, r, t_min, eo.b.cap, kRefillLanes);
+    else k_traverse<false><<<segments, kBlock, 0, stream>>>(ctl, sr, ds, tq, r, t_min, eo.b.cap, kRefillLanes);
+    k_extend_post<<<segments, kBlock, 0, stream>>>(sr, ds, eo, tq, r, t_min, t_max);
   }
-  return launches;
+  return 1 + 2 * rounds;
 }
 
 void require_committed(const ptc_scene *s) {
@@ -264,51 +265,96 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
     return s->timing_events[tev_used++];
   };
   std::vector<int> mark_stage;
-  const std::function<void(int)> mark = [&](int stage) {
+  const auto mark = [&](int stage) {
     CK(cudaEventRecord(tev(), stream));
     mark_stage.push_back(stage);
   };
 
   CK(cudaEventRecord(ev_begin, stream));
-  // initial fill: a shade pass over empty segments is pure regeneration
-  if (timing) mark(ST_SHADE);
-  k_shade<<<segments, kBlock, kShadeSmem, stream>>>(s->d_ctl.p, s->ds, rp, b, d_accum);
-  uint64_t launches = 1;
-  std::deque<int> pending;
-  int ring_next = 0;
-  uint64_t it = 0;
-  const int check_every = 4;
-  bool finished = init.total_paths == 0;
-  auto is_done = [](const Ctl &c) { return c.n_live == 0 && c.next_path >= c.total_paths; };
-  while (!finished) {
-    const ExtendOut eo{b, nullptr};
-    launches += launch_extend(stream, segments, rounds, s->d_ctl.p, s->ds, eo, tq, kEps, INFINITY, counters, timing ? &mark : nullptr);
-    if (timing) mark(ST_SHADE);
-    k_shade<<<segments, kBlock, kShadeSmem, stream>>>(s->d_ctl.p, s->ds, rp, b, d_accum);
-    launches += 1;
-    it++;
-    if (it % check_every == 0) {
-      // snapshot the control block; consume finished snapshots without stalling the launch queue.  The host only
-      // blocks when the ring is full, i.e. when it is kRing * check_every iterations ahead of what it has seen.
-      const int k = ring_next;
-      ring_next = (ring_next + 1) % ptc_scene::kRing;
-      CK(cudaMemcpyAsync(&s->h_ctl[k], s->d_ctl.p, sizeof(Ctl), cudaMemcpyDeviceToHost, stream));
-      CK(cudaEventRecord(s->ring_ev[k], stream));
-      pending.push_back(k);
-      while (!pending.empty()) {
-        const int o = pending.front();
-        const bool must_wait = (int)pending.size() >= ptc_scene::kRing;
-        if (!must_wait && cudaEventQuery(s->ring_ev[o]) == cudaErrorNotReady) {
-          cudaGetLastError();
-          break;
+  uint64_t launches = 0;
+  static const bool persistent = getenv("PTC_PERSISTENT") != nullptr;  // measured dead end, kept for the record
+  static const bool two_streams = getenv("PTC_TWO_STREAMS") != nullptr;  // measured: no gain, kept as a knob
+  static const uint32_t refill = getenv("PTC_REFILL") ? (uint32_t)atoi(getenv("PTC_REFILL")) : kRefillLanes;
+  auto is_done = [](const Ctl &c) { return c.n_live[0] == 0 && c.n_live[1] == 0 && c.next_path >= c.total_paths; };
+  if (persistent && !timing && !counters) {
+    k_wavefront<<<segments, kBlock, kShadeSmem, stream>>>(s->d_ctl.p, s->ds, rp, b, tq, rounds, d_accum, refill);
+    launches = 1;
+  } else if (init.total_paths != 0) {
+    // Optionally two half-wavefronts on two streams, so that the kernel tails of one half could be filled by the other;
+    // measured on B200 this does not beat a single stream, so it is off unless asked for.
+    const int halves = (two_streams && !timing && segments >= 2) ? 2 : 1;
+    cudaStream_t hs[2] = {stream, s->aux_stream};
+    SegRange sr[2];
+    uint32_t blocks[2];
+    blocks[0] = halves == 2 ? segments / 2 : segments;
+    blocks[1] = segments - blocks[0];
+    sr[0] = SegRange{0u, segments, 0u};
+    sr[1] = SegRange{blocks[0], segments, 1u};
+    if (halves == 2) {  // the second stream starts after the control block and the counts are reset
+      CK(cudaEventRecord(s->fork_ev, stream));
+      CK(cudaStreamWaitEvent(hs[1], s->fork_ev, 0));
+    }
+    auto run_extend = [&](int h) {
+      const ExtendOut eo{b, nullptr};
+      if (timing) mark(ST_PRE);
+      k_extend_pre<<<blocks[h], kBlock, 0, hs[h]>>>(s->d_ctl.p, sr[h], s->ds, eo, tq, kEps, INFINITY);  // renderer.rs:24
+      for (int r = 0; r < rounds; r++) {
+        if (timing) mark(ST_TRAVERSE);
+        if (counters) k_traverse<true><<<blocks[h], kBlock, 0, hs[h]>>>(s->d_ctl.p, sr[h], s->ds, tq, r, kEps, b.cap, refill);
+        else k_traverse<false><<<blocks[h], kBlock, 0, hs[h]>>>(s->d_ctl.p, sr[h], s->ds, tq, r, kEps, b.cap, refill);
+        if (timing) mark(ST_POST);
+        k_extend_post<<<blocks[h], kBlock, 0, hs[h]>>>(sr[h], s->ds, eo, tq, r, kEps, INFINITY);
+      }
+      launches += 1 + 2 * (uint64_t)rounds;
+    };
+    auto run_shade = [&](int h) {
+      if (timing) mark(ST_SHADE);
+      k_shade<<<blocks[h], kBlock, kShadeSmem, hs[h]>>>(s->d_ctl.p, sr[h], s->ds, rp, b, d_accum);
+      launches += 1;
+    };
+    for (int h = 0; h < halves; h++) run_shade(h);  // initial fill: a shade pass over empty segments is pure regeneration
+    std::deque<int> pending;
+    int ring_next = 0;
+    uint64_t it = 0;
+    const int check_every = 4;
+    bool finished = false;
+    while (!finished) {
+      for (int h = 0; h < halves; h++) {
+        run_extend(h);
+        run_shade(h);
+      }
+      it++;
+      if (it % check_every == 0) {
+        // snapshot the control block (after both halves' work so far); consume finished snapshots without stalling the
+        // launch queue.  The host only blocks when the ring is full.
+        const int k = ring_next;
+        ring_next = (ring_next + 1) % ptc_scene::kRing;
+        if (halves == 2) {
+          CK(cudaEventRecord(s->join_ev, hs[1]));
+          CK(cudaStreamWaitEvent(stream, s->join_ev, 0));
         }
-        CK(cudaEventSynchronize(s->ring_ev[o]));
-        pending.pop_front();
-        if (is_done(s->h_ctl[o])) {
-          finished = true;
-          break;
+        CK(cudaMemcpyAsync(&s->h_ctl[k], s->d_ctl.p, sizeof(Ctl), cudaMemcpyDeviceToHost, stream));
+        CK(cudaEventRecord(s->ring_ev[k], stream));
+        pending.push_back(k);
+        while (!pending.empty()) {
+          const int o = pending.front();
+          const bool must_wait = (int)pending.size() >= ptc_scene::kRing;
+          if (!must_wait && cudaEventQuery(s->ring_ev[o]) == cudaErrorNotReady) {
+            cudaGetLastError();
+            break;
+          }
+          CK(cudaEventSynchronize(s->ring_ev[o]));
+          pending.pop_front();
+          if (is_done(s->h_ctl[o])) {
+            finished = true;
+            break;
+          }
         }
       }
+    }
+    if (halves == 2) {  // join before the end-of-render event
+      CK(cudaEventRecord(s->join_ev, hs[1]));
+      CK(cudaStreamWaitEvent(stream, s->join_ev, 0));
     }
   }
   CK(cudaGetLastError());
@@ -316,12 +362,12 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
   CK(cudaMemcpyAsync(&s->h_ctl[0], s->d_ctl.p, sizeof(Ctl), cudaMemcpyDeviceToHost, stream));
   CK(cudaStreamSynchronize(stream));
   const Ctl fin = s->h_ctl[0];
-  if (!is_done(fin)) throw std::runtime_error("wavefront loop ended before all paths terminated");
+  if (!(fin.next_path >= fin.total_paths) || (!persistent && !is_done(fin))) throw std::runtime_error("wavefront loop ended before all paths terminated");
   if (stats) {
     memset(stats, 0, sizeof(*stats));
     stats->paths = rp.max_depth > 0 ? my_pixels * (uint64_t)rp.n_samples : 0;
     stats->rays = fin.rays;
-    stats->iterations = fin.iterations;
+    stats->iterations = std::max(fin.iterations[0], fin.iterations[1]);
     stats->kernel_launches = launches;
     float ms = 0.0f;
     CK(cudaEventElapsedTime(&ms, ev_begin, ev_end));
@@ -500,6 +546,9 @@ int ptc_scene_commit(ptc_scene *s, int device) {
   for (const DObject &o : s->hs.objects)
     if (o.type == OBJ_MESH) s->mesh_objects++;
   CK(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&s->aux_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&s->fork_ev, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&s->join_ev, cudaEventDisableTiming));
   s->committed = true;
   return 0;
   PTC_GUARD_END
