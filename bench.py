@@ -58,7 +58,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except OSError:
@@ -243,17 +243,21 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_total, stats = timed(lambda: step_device(pt.FLAG_TIMING), args.steps)
+    # `value`: the production path, exactly K steps.  Then K more steps of the same work with PTC_FLAG_TIMING, which
+    # brackets every stage launch with CUDA events on the launching stream (a few per cent slower): these give the
+    # per-kernel share and the roofline's launch durations.  Clocks are sampled across both.
+    ms_total, vstats = timed(lambda: step_device(0), args.steps)
+    _, stats = timed(lambda: step_device(pt.FLAG_TIMING), args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
-    paths_rank = sum(s.paths for s in stats)
-    rays_rank = sum(s.rays for s in stats)
+    paths_rank = sum(s.paths for s in vstats)
+    rays_rank = sum(s.rays for s in vstats)
     cnt = torch.tensor([paths_rank, rays_rank], dtype=torch.float64, device=dev)
     if dist:
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     paths_all, rays_all = float(cnt[0].item()), float(cnt[1].item())
     value = paths_all / ms_total / 1e3
-    launches = sum(s.kernel_launches for s in stats) + args.steps * 2  # + memset + resolve
+    launches = sum(s.kernel_launches for s in vstats) + args.steps * 2  # + memset + resolve
 
     for _ in range(2):
         step_e2e()

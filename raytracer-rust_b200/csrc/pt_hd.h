@@ -69,6 +69,8 @@ PT_HD float4 ldg4(const float4 *p) {
   return *p;
 #endif
 }
+// plain 16-byte load: the object table may have been staged into shared memory, where ld.global.nc must not be used
+PT_HD float4 ld4(const float4 *p) { return *p; }
 PT_HD bool isnan_f(float v) { return v != v; }
 PT_HD bool isinf_f(float v) { return fabsf(v) == INFINITY; }
 

@@ -95,7 +95,7 @@ struct M4 {
 };
 PT_HD M4 load_m4(const float *m) {  // m must be 16-byte aligned (DObject::f is)
   const float4 *p = reinterpret_cast<const float4 *>(m);
-  return M4{ldg4(p), ldg4(p + 1), ldg4(p + 2), ldg4(p + 3)};
+  return M4{ld4(p), ld4(p + 1), ld4(p + 2), ld4(p + 3)};
 }
 PT_HD V3 mat_point(const M4 &m, V3 p) {
   V3 r;

@@ -25,7 +25,7 @@ PT_HD void set_pos(Hit &h, V3 p) {
 
 // src/objects/sphere.rs:15-53
 PT_HD bool hit_sphere(const float *f, const Ray &ray, float t_min, float t_max, Hit &h) {
-  const float4 cr = ldg4(reinterpret_cast<const float4 *>(f));
+  const float4 cr = ld4(reinterpret_cast<const float4 *>(f));
   const V3 center = v3(cr.x, cr.y, cr.z);
   const float radius = cr.w;
   const V3 oc = ray.o - center;
@@ -64,7 +64,7 @@ PT_HD bool hit_plane(const float *f, const Ray &ray, float t_min, float t_max, H
 // src/tungsten/objects/quad.rs:83-132
 PT_HD bool hit_quad(const float *f, const Ray &ray, float t_min, float t_max, Hit &h) {
   const float4 *f4 = reinterpret_cast<const float4 *>(f);
-  const float4 q0 = ldg4(f4), q1 = ldg4(f4 + 1), q2 = ldg4(f4 + 2), q3 = ldg4(f4 + 3);
+  const float4 q0 = ld4(f4), q1 = ld4(f4 + 1), q2 = ld4(f4 + 2), q3 = ld4(f4 + 3);
   const V3 base = v3(q0.x, q0.y, q0.z), e0 = v3(q0.w, q1.x, q1.y), e1 = v3(q1.z, q1.w, q2.x), n = v3(q2.y, q2.z, q2.w);
   const float d = q3.x, inv0 = q3.y, inv1 = q3.z;
   const float denom = dot(n, ray.d);

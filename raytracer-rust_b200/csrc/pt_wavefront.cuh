@@ -106,10 +106,10 @@ __device__ __forceinline__ void write_miss(const ExtendOut &out, uint32_t i) {
 // interval convention.  Returns the index of the mesh the ray has to be parked at (its object-space ray in
 // `park_ray`), or -1 when the scan is complete.  Every object sees exactly the `closest` it would have seen in the
 // reference's sequential scan, so tie-breaking is untouched by the parking.
-__device__ __forceinline__ int scan_objects(const DScene &sc, const Ray &ray, float t_min, float &closest, Hit &best,
-                                            bool &improved, int k_begin, MeshRay &park_ray) {
+__device__ __forceinline__ int scan_objects(const DScene &sc, const DObject *objs, const Ray &ray, float t_min, float &closest,
+                                            Hit &best, bool &improved, int k_begin, MeshRay &park_ray) {
   for (int k = k_begin; k < sc.n_objects; k++) {
-    const DObject *ob = sc.objects + k;
+    const DObject *ob = objs + k;
     const int type = ob->type;
     Hit tmp;
     tmp.triangle = -1;
@@ -135,6 +135,18 @@ __device__ __forceinline__ int scan_objects(const DScene &sc, const Ray &ray, fl
   return -1;
 }
 
+// The object table is read by every lane for every ray; ray data streaming through L1 kept evicting it (the load of
+// `ob->type` alone was 12 % of k_extend_pre's stall samples), so each block stages it into shared memory once.
+constexpr int kSmemObjects = 24;
+__device__ __forceinline__ const DObject *stage_objects(const DScene &sc, DObject *s_objs) {
+  if (sc.n_objects > kSmemObjects) return sc.objects;
+  const uint4 *src = reinterpret_cast<const uint4 *>(sc.objects);
+  uint4 *dst = reinterpret_cast<uint4 *>(s_objs);
+  const int n16 = sc.n_objects * (int)(sizeof(DObject) / 16);
+  for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
+  return s_objs;  // visible after the caller's __syncthreads()
+}
+
 // Append the parked lanes of this warp to the block's task segment: ballot + one SHARED-memory atomic per warp.
 __device__ __forceinline__ void park_tasks(uint32_t *s_ntask, const TaskQ &tq, int par, uint32_t seg_base, int park, uint32_t i,
                                            const MeshRay &mr, float closest) {
@@ -158,9 +170,11 @@ __device__ __forceinline__ void park_tasks(uint32_t *s_ntask, const TaskQ &tq, i
 __device__ __forceinline__ void stage_pre(uint32_t seg, uint32_t n_seg, const DScene &sc, const ExtendOut &out, const TaskQ &tq,
                                           float t_min, float t_max) {
   __shared__ uint32_t s_ntask;
+  __shared__ __align__(16) DObject s_objs[kSmemObjects];
   const uint32_t tid = threadIdx.x;
   const uint32_t n = out.b.cnt[seg], seg_base = seg * out.b.cap;
   if (tid == 0) s_ntask = 0;
+  const DObject *objs = stage_objects(sc, s_objs);
   __syncthreads();
   for (uint32_t c0 = 0; c0 < n; c0 += (uint32_t)kBlock) {
     const uint32_t i = seg_base + c0 + tid;
@@ -172,7 +186,7 @@ __device__ __forceinline__ void stage_pre(uint32_t seg, uint32_t n_seg, const DS
       const Ray ray{v3(o4.x, o4.y, o4.z), v3(d4.x, d4.y, d4.z)};
       Hit best;
       bool improved = false;
-      park = scan_objects(sc, ray, t_min, closest, best, improved, 0, mr);  // renderer.rs:24
+      park = scan_objects(sc, objs, ray, t_min, closest, best, improved, 0, mr);  // renderer.rs:24
       if (improved) write_hit(out, i, best);
       else write_miss(out, i);
     }
@@ -255,10 +269,12 @@ __device__ __forceinline__ void stage_traverse(uint32_t seg, uint32_t n_seg, Ctl
 __device__ __forceinline__ void stage_post(uint32_t seg, uint32_t n_seg, const DScene &sc, const ExtendOut &out, const TaskQ &tq,
                                            int round, float t_min, float t_max) {
   __shared__ uint32_t s_ntask;
+  __shared__ __align__(16) DObject s_objs[kSmemObjects];
   const uint32_t tid = threadIdx.x;
   const uint32_t n = tq.cnt[(uint32_t)round * n_seg + seg], seg_base = seg * out.b.cap;
   const int par = round & 1;
   if (tid == 0) s_ntask = 0;
+  const DObject *objs = stage_objects(sc, s_objs);
   __syncthreads();
   for (uint32_t c0 = 0; c0 < n; c0 += (uint32_t)kBlock) {
     const uint32_t j = seg_base + c0 + tid;
@@ -280,7 +296,7 @@ __device__ __forceinline__ void stage_post(uint32_t seg, uint32_t n_seg, const D
       bool improved = false;
       const uint32_t tri = f2u(res.y);
       if (tri != 0xffffffffu) {
-        const DObject *ob = sc.objects + k;
+        const DObject *ob = objs + k;
         const MeshRay omr = mesh_object_ray(ob->f, ray);  // same inputs, same bits as in k_extend_pre
         MeshHit mh;
         mh.t = res.x, mh.tri = tri, mh.order = 0u;
@@ -293,7 +309,7 @@ __device__ __forceinline__ void stage_post(uint32_t seg, uint32_t n_seg, const D
           best.material = ob->material;
         }
       }
-      park = scan_objects(sc, ray, t_min, closest, best, improved, k + 1, mr);
+      park = scan_objects(sc, objs, ray, t_min, closest, best, improved, k + 1, mr);
       if (improved) write_hit(out, i, best);  // otherwise the record parked by the previous stage stands
     }
     park_tasks(&s_ntask, tq, par ^ 1, seg_base, park, i, mr, closest);

@@ -51,3 +51,10 @@ def test_small_meshes(pt):
 def test_synthetic_heightfield(pt):
     # C5's generator at 256x256 cells = 131,072 triangles (the full 2 M-triangle build is exercised by the bench tools)
     pc.check_synthetic_heightfield(KIND, pt, cells=256, n=200000)
+
+
+def test_synthetic_heightfield_full_size(pt):
+    # BASELINE config C5's mesh at its full size: 1000x1000 cells = 2,000,000 triangles (299 k wide nodes, 96 MB of
+    # triangles); primary rays + 300 k random rays, every hit record bit-identical to the oracle's
+    r, stats = pc.check_synthetic_heightfield(KIND, pt, cells=1000, n=300000)
+    assert stats.mesh_rays > 0 and stats.nodes_visited / stats.mesh_rays > 4
