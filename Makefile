@@ -26,8 +26,8 @@ $(PKG)/libpthost.so: $(PKG)/host/pthost.cpp $(PKG)/host/json.hpp $(PKG)/libptcor
 oracle/liboracle.so: oracle/oracle.cpp oracle/oracle.h
 	$(MAKE) -C oracle
 
-tests/hostsim/libhostsim.so: tests/hostsim/hostsim.cpp $(CSRC)/pt_build.cpp $(HDRS)
-	$(CXX) $(CXXFLAGS) -shared -o $@ tests/hostsim/hostsim.cpp $(CSRC)/pt_build.cpp
+tests/hostsim/libhostsim.so: tests/hostsim/hostsim.cpp tests/hostsim/wfsim.cpp $(CSRC)/pt_build.cpp $(HDRS)
+	$(CXX) $(CXXFLAGS) -shared -o $@ tests/hostsim/hostsim.cpp tests/hostsim/wfsim.cpp $(CSRC)/pt_build.cpp
 
 clean:
 	rm -f $(PKG)/libptcore.so $(PKG)/libpthost.so oracle/liboracle.so tests/hostsim/libhostsim.so

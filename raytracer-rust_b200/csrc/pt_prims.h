@@ -140,7 +140,7 @@ PT_HD MeshRay mesh_object_ray(const float *w2o_f, const Ray &ray) {
 // Conservative pre-test against the padded frame of the root node: false only if no live triangle can be hit in
 // (t_min, t_max).  Same NaN-dropping slab arithmetic as the node test in pt_bvh8.h.
 PT_HD bool mesh_root_may_hit(const DMesh &mesh, const MeshRay &r, float t_min, float t_max) {
-  const float idx = 1.0f / r.d.x, idy = 1.0f / r.d.y, idz = 1.0f / r.d.z;
+  const float idx = box_rcp(r.d.x), idy = box_rcp(r.d.y), idz = box_rcp(r.d.z);  // conservative test: no IEEE division needed
   const float ax = (mesh.root_lo[0] - r.o.x) * idx, bx = (mesh.root_hi[0] - r.o.x) * idx;
   const float ay = (mesh.root_lo[1] - r.o.y) * idy, by = (mesh.root_hi[1] - r.o.y) * idy;
   const float az = (mesh.root_lo[2] - r.o.z) * idz, bz = (mesh.root_hi[2] - r.o.z) * idz;

@@ -9,15 +9,17 @@
 //   k_traverse     persistent warps over the block's tasks: each lane walks its own BVH one step at a time, idle lanes
 //                  refetch from the block's cursor
 //   k_extend_post  second half of Mesh::hit + rest of the object list for every task; may park again (next round)
-//   k_shade        stages 256-ray chunks of the segment through shared memory with TMA bulk copies, counting-sorts each
-//                  chunk by material, shades, writes the survivors back IN PLACE at the front of the segment, then
-//                  REGENERATES: tops the segment up with fresh camera paths (Philox jitter + Camera::get_ray)
+//   k_shade        counting-sorts 2048-ray windows of the segment by material class (keys only, in shared memory), every
+//                  warp shades 8 class-homogeneous 32-ray groups spread over the sorted window (gathered straight from
+//                  global memory), survivors go to the front of the segment's OTHER ray buffer (ping-pong), then the
+//                  block REGENERATES: tops the segment up with fresh camera paths (Philox jitter + Camera::get_ray)
 //
 // Consequences: no global compaction, no global queue cursor — the only same-address global atomics left are one
 // `next_path` reservation and one `n_live` add per block and iteration (per-warp atomics on single counters were 16-56 %
 // of the stall samples of the previous design, profiles/r1_v3_*); ray state is single-buffered; each block's working
 // set stays in its own slice of memory; when the path supply runs out all segments drain together, so the tail needs
-// no repacking either.
+// no repacking either.  (A persistent one-kernel variant and a two-stream variant of this loop were measured slower on
+// B200 and removed; DESIGN.md section 5 keeps the numbers.)
 //
 // Only Emissive surfaces and the sky carry radiance and both end the path (EmissiveLight::scatter is None), so a path
 // contributes beta * Le exactly once, when it terminates: one float RED triple per path into the film.
@@ -46,13 +48,11 @@ struct Ctl {
   uint32_t iterations[2];  // per half-wavefront
 };
 
-// The segments are split into two halves that run the same sequence of stage kernels on two streams, half an iteration
-// apart in practice: while one half is in its (ALU-bound, ragged-tailed) traversal the other is in its (latency-bound)
-// shading, so the tails of one fill with the other's work.  A kernel launch covers segments [seg0, seg0 + gridDim.x).
+// A kernel launch covers segments [seg0, seg0 + gridDim.x).
 struct SegRange {
   uint32_t seg0;   // first segment of this launch
   uint32_t n_seg;  // segments of the whole pool (stride of the task-count table)
-  uint32_t half;   // 0 / 1
+  uint32_t half;   // index into Ctl::n_live / iterations (always 0 today)
 };
 
 struct RenderParams {
@@ -74,6 +74,8 @@ struct Buffers {
   float4 *hit1;   // normal.xyz, [hit<<31 | front_face<<30 | material]
   uint32_t *cnt;  // [S]
   uint32_t cap;   // multiple of kBlock
+  // the ray arrays the shade stage writes (survivors + regenerated paths); the host swaps the two sets every iteration
+  float4 *nray_o, *nray_d, *nbeta;
 };
 
 struct ExtendOut {
@@ -318,34 +320,9 @@ __device__ __forceinline__ void stage_post(uint32_t seg, uint32_t n_seg, const D
   if (tid == 0) tq.cnt[(uint32_t)(round + 1) * n_seg + seg] = s_ntask;
 }
 
-// ---- sm_100a asynchronous bulk copy (TMA, 1-D) + mbarrier, raw PTX ----
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-// global -> shared, completion (byte count) signalled on the mbarrier; SASS: UBLKCP
-__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
-               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
-constexpr int kShadeClasses = 10;  // 0 = miss, 1 + material type (8 types), 9 = no ray (tail of the last chunk)
-constexpr int kShadeArrays = 5;    // ray_o, ray_d, beta, hit0, hit1
-constexpr size_t kShadeSmem = 2 * kShadeArrays * kBlock * sizeof(float4) + 128;  // two staged chunks + alignment slack
+constexpr int kShadeClasses = 10;  // 0 = miss, 1 + material type (8 types), 9 = no ray (tail of the last window)
+constexpr int kShadeWindow = 2048;                   // rays one block sorts together
+constexpr int kShadeGroups = kShadeWindow / kBlock;  // 32-ray groups each warp shades per window
 
 // Block-wide exclusive offsets for a per-thread flag: ranks from the warp ballot, warp totals through shared memory.
 // Returns this thread's offset (valid if `flag`); *total = number of flagged threads.  Two block barriers.
@@ -369,150 +346,149 @@ __device__ __forceinline__ uint32_t block_rank(bool flag, uint32_t *s_warp /* [k
 }
 
 // shade (+ regenerate): emitted + scatter (renderer.rs:26-36) or sky (renderer.rs:38-63) for every ray of the segment,
-// survivors written back in place; then fresh camera paths (renderer.rs:96-99, camera.rs:33-42) fill the free slots.
+// survivors written to the front of the segment in the other ray buffer; then fresh camera paths (renderer.rs:96-99,
+// camera.rs:33-42) fill the free slots.
 //
 // Rays arrive in no particular order, so a warp would see a mix of misses and of every material and run all of their
-// code (measured: 11.5 of 32 lanes active), and waiting for one's own loads leaves the kernel latency-bound.  Hence a
-// two-stage pipeline over 256-ray chunks:
-//   * one thread issues five 1-D bulk async copies (TMA; ray_o, ray_d, beta, hit0, hit1 slices, 4 KB each) of the NEXT
-//     chunk into shared memory, completion counted on an mbarrier, while the block shades the current one;
-//   * the current chunk is counting-sorted by (miss | material type) in shared memory; thread t shades the t-th ray of
-//     that order straight out of the staged copy, so warps are homogeneous except at class boundaries;
-//   * survivors go to the front of the segment (block-local cursor; always behind the chunk being read, and the chunk
-//     itself is already staged, so in place is safe).
-// `s_raw` = the two staged chunks [2][5][256] float4 (dynamic shared memory), `s_bar` = their two mbarriers (initialised
-// by the calling kernel), `used[b]` = how many times stage b has been waited on so far (its mbarrier phase parity).
+// code (measured: 11.5 of 32 lanes active).  The first remedy (round 1, v2) sorted 256-ray chunks staged in shared
+// memory by TMA bulk copies; its profile showed 43 % of the stall samples on block barriers: the eight 32-ray groups of
+// a chunk are homogeneous, hence of very different cost (a group of misses is a few instructions, a group of rough
+// conductors several hundred), and every chunk ended with the whole block waiting for its most expensive group (the
+// SIMT model in tests/hostsim/wfsim.cpp puts the barrier-synchronous cost at 2.3-3x the sum of the group costs).  Now:
+//   * a WINDOW of 2048 rays is counting-sorted by (miss | material type) — keys only: one 16-byte load of hit1 per ray,
+//     warp-aggregated shared-memory atomics for the position inside the class, two block barriers per window;
+//   * warp w shades groups w, w + 8, ..., w + 56 of the sorted window: eight groups spread over all classes, so the
+//     warps of a block carry nearly equal work and nobody waits; the larger window also leaves fewer mixed groups
+//     (model: lane efficiency 0.77 -> 0.93 on C2);
+//   * a thread gathers its ray (five 16-byte loads) straight from global memory.  The window is block-local (160 KB of
+//     contiguous slots), so the other half of every 32-byte sector is consumed by a neighbour warp of the same block
+//     out of L1/L2: no extra DRAM traffic, and no staging buffers, mbarriers or proxy fences;
+//   * survivors are appended at a block-local cursor (one shared-memory atomic per warp) in the OTHER ray buffer:
+//     with gathers in flight all over the window, compaction in place would overwrite rays that are still to be read.
 // Returns the new ray count of the segment.
 __device__ __forceinline__ uint32_t stage_shade(uint32_t seg, uint32_t half, Ctl *ctl, const DScene &sc, const RenderParams &rp, const Buffers &b,
-                                                float *accum, float4 *s_raw, uint64_t *s_bar, uint32_t (&used)[2]) {
-  __shared__ uint16_t s_perm[kBlock];
-  __shared__ uint32_t s_cnt[kBlock / 32][kShadeClasses];
-  __shared__ uint32_t s_off[kBlock / 32][kShadeClasses];
+                                                float *accum) {
+  __shared__ uint16_t s_perm[kShadeWindow];
+  __shared__ uint32_t s_hist[2][16];
   __shared__ uint32_t s_warp[kBlock / 32 + 1];
   __shared__ unsigned long long s_first;
-  __shared__ uint32_t s_avail, s_more;
+  __shared__ uint32_t s_avail, s_more, s_w;
   const uint32_t n = b.cnt[seg], seg_base = seg * b.cap;
-  const uint32_t n_chunks = (n + (uint32_t)kBlock - 1) / (uint32_t)kBlock;
-  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-  const float4 *g_arr[kShadeArrays] = {b.ray_o + seg_base, b.ray_d + seg_base, b.beta + seg_base, b.hit0 + seg_base, b.hit1 + seg_base};
-
-  auto issue = [&](uint32_t chunk, uint32_t buf) {  // one thread
-    const uint32_t first = chunk * (uint32_t)kBlock;
-    const uint32_t cnt = n - first < (uint32_t)kBlock ? n - first : (uint32_t)kBlock;
-    const uint32_t bytes = cnt * (uint32_t)sizeof(float4);
-    mbar_expect_tx(&s_bar[buf], bytes * kShadeArrays);
-#pragma unroll
-    for (int a = 0; a < kShadeArrays; a++)
-      bulk_g2s(s_raw + ((size_t)buf * kShadeArrays + a) * kBlock, g_arr[a] + first, bytes, &s_bar[buf]);
-  };
-
-  // hit records written with ordinary stores by the extend stages of this same kernel must be visible to the bulk copy
-  // engine (async proxy)
-  asm volatile("fence.proxy.async;" ::: "memory");
+  const uint32_t tid = threadIdx.x, lane = tid & 31u;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  if (tid == 0) s_w = 0u;
+  if (tid < 32u) s_hist[0][tid & 15u] = 0u, s_hist[1][tid & 15u] = 0u;
   __syncthreads();
-  if (tid == 0 && n_chunks > 0) issue(0, 0);
 
-  uint32_t w = 0;  // survivors written so far = write cursor inside the segment (same value in every thread)
-  for (uint32_t chunk = 0; chunk < n_chunks; chunk++) {
-    const uint32_t buf = chunk & 1u;
-    // the other stage was last read in the previous iteration, which ended with a block barrier
-    if (tid == 0 && chunk + 1 < n_chunks) issue(chunk + 1, buf ^ 1u);
-    const uint32_t first = chunk * (uint32_t)kBlock;
-    const uint32_t in_chunk = n - first < (uint32_t)kBlock ? n - first : (uint32_t)kBlock;
-    const float4 *raw = s_raw + (size_t)buf * kShadeArrays * kBlock;
-    mbar_wait(&s_bar[buf], used[buf] & 1u);
-    used[buf]++;
-
-    uint32_t key = kShadeClasses - 1;
-    if (tid < in_chunk) {
-      const uint32_t bits0 = f2u(raw[4 * kBlock + tid].w);
-      key = (bits0 & kHitBit) ? 1u + (uint32_t)sc.materials[bits0 & kMatMask].type : 0u;
-    }
-    uint32_t rank = 0;
+  uint32_t parity = 0;
+  for (uint32_t w0 = 0; w0 < n; w0 += (uint32_t)kShadeWindow, parity ^= 1u) {
+    const uint32_t wn = n - w0 < (uint32_t)kShadeWindow ? n - w0 : (uint32_t)kShadeWindow;
+    const uint32_t win_base = seg_base + w0;
+    // ---- pass 1: class key and position inside the class for the thread's 8 rays
+    uint32_t keypos[kShadeGroups];
 #pragma unroll
-    for (uint32_t c = 0; c < (uint32_t)kShadeClasses; c++) {
-      const uint32_t m = __ballot_sync(0xffffffffu, key == c);
-      if (key == c) rank = (uint32_t)__popc(m & ((1u << lane) - 1u));
-      if (lane == 0) s_cnt[warp][c] = (uint32_t)__popc(m);
+    for (int r = 0; r < kShadeGroups; r++) {
+      const uint32_t idx = (uint32_t)r * kBlock + tid;
+      uint32_t key = kShadeClasses - 1;
+      if (idx < wn) {
+        const uint32_t bits = f2u(__ldg(&b.hit1[win_base + idx]).w);
+        key = (bits & kHitBit) ? 1u + (uint32_t)__ldg(&sc.materials[bits & kMatMask].type) : 0u;
+      }
+      const uint32_t peers = __match_any_sync(0xffffffffu, key);
+      const int leader = __ffs((int)peers) - 1;
+      uint32_t base = 0;
+      if ((int)lane == leader) base = atomicAdd(&s_hist[parity][key], (uint32_t)__popc(peers));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      keypos[r] = key | ((base + (uint32_t)__popc(peers & lt_mask)) << 4);
     }
     __syncthreads();
-    if (warp == 0) {
-      uint32_t tot = 0;
-      if (lane < (uint32_t)kShadeClasses)
-        for (int ww = 0; ww < kBlock / 32; ww++) tot += s_cnt[ww][lane];
-      uint32_t incl = tot;  // inclusive scan over the classes
+    if (tid < 16u) s_hist[parity ^ 1u][tid] = 0u;  // free since barrier 2 of the previous window, next used after barrier 2 below
+    {
+      const uint32_t h = lane < (uint32_t)kShadeClasses ? s_hist[parity][lane] : 0u;
+      uint32_t incl = h;  // inclusive scan over the classes
 #pragma unroll
       for (int d = 1; d < 16; d <<= 1) {
         const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
         if (lane >= (uint32_t)d) incl += v;
       }
-      if (lane < (uint32_t)kShadeClasses) {
-        uint32_t off = incl - tot;
-        for (int ww = 0; ww < kBlock / 32; ww++) {
-          s_off[ww][lane] = off;
-          off += s_cnt[ww][lane];
-        }
+      const uint32_t excl = incl - h;
+#pragma unroll
+      for (int r = 0; r < kShadeGroups; r++) {
+        const uint32_t key = keypos[r] & 15u;
+        const uint32_t off = __shfl_sync(0xffffffffu, excl, (int)key);
+        if (key != (uint32_t)kShadeClasses - 1u) s_perm[off + (keypos[r] >> 4)] = (uint16_t)((uint32_t)r * kBlock + tid);
       }
     }
-    __syncthreads();
-    s_perm[s_off[warp][key] + rank] = (uint16_t)tid;
     __syncthreads();
 
-    bool alive = false;
-    float4 no, nd, nb;
-    if (tid < in_chunk) {  // the "no ray" class sorts last
-      const uint32_t j = s_perm[tid];
-      const float4 o4 = raw[0 * kBlock + j], d4 = raw[1 * kBlock + j], b4 = raw[2 * kBlock + j];
-      const float4 h1 = raw[4 * kBlock + j];
-      const uint32_t pixel = f2u(o4.w), sample = f2u(d4.w), bounce = f2u(b4.w);
-      const uint32_t bits = f2u(h1.w);
-      const V3 beta = v3(b4.x, b4.y, b4.z);
-      const V3 ray_d = v3(d4.x, d4.y, d4.z);
-      V3 radiance = v3(0, 0, 0);
-      bool add = false;
-      if (!(bits & kHitBit)) {
-        radiance = beta * sky_color(sc, ray_d);
-        add = true;
-      } else {
-        const float4 h0 = raw[3 * kBlock + j];
-        const DMaterial m = sc.materials[bits & kMatMask];
-        const V3 e = mat_emitted(m);
-        if (e.x != 0.0f || e.y != 0.0f || e.z != 0.0f) {
-          radiance = beta * e;
+    // ---- pass 2: the t-th thread of group g shades the (g * 256 + t)-th ray of the sorted window
+#pragma unroll 1
+    for (int g = 0; g < kShadeGroups; g++) {
+      const uint32_t p = (uint32_t)g * kBlock + tid;
+      if ((uint32_t)g * kBlock >= wn) break;
+      bool alive = false;
+      float4 no, nd, nb;
+      if (p < wn) {
+        const uint32_t i = win_base + (uint32_t)s_perm[p];
+        const float4 o4 = __ldg(&b.ray_o[i]), d4 = __ldg(&b.ray_d[i]), b4 = __ldg(&b.beta[i]);
+        const float4 h1 = __ldg(&b.hit1[i]);
+        const uint32_t pixel = f2u(o4.w), sample = f2u(d4.w), bounce = f2u(b4.w);
+        const uint32_t bits = f2u(h1.w);
+        const V3 beta = v3(b4.x, b4.y, b4.z);
+        const V3 ray_d = v3(d4.x, d4.y, d4.z);
+        V3 radiance = v3(0, 0, 0);
+        bool add = false;
+        if (!(bits & kHitBit)) {
+          radiance = beta * sky_color(sc, ray_d);
           add = true;
-        }
-        const Uniforms4 u = philox_uniforms(rp.seed, pixel, sample, bounce, 0u);
-        Ray sc_ray;
-        V3 att;
-        if (mat_scatter(m, ray_d, v3(h0.x, h0.y, h0.z), v3(h1.x, h1.y, h1.z), (bits & kFrontBit) != 0u, u.u, sc_ray, att)) {
-          // trace_ray(scattered, depth - 1): depth 0 returns black (renderer.rs:20-22)
-          if (bounce + 1u < (uint32_t)rp.max_depth) {
-            alive = true;
-            const V3 nbeta = beta * att;
-            no = make_float4(sc_ray.o.x, sc_ray.o.y, sc_ray.o.z, o4.w);
-            nd = make_float4(sc_ray.d.x, sc_ray.d.y, sc_ray.d.z, d4.w);
-            nb = make_float4(nbeta.x, nbeta.y, nbeta.z, u2f(bounce + 1u));
+        } else {
+          const float4 h0 = __ldg(&b.hit0[i]);
+          const DMaterial m = sc.materials[bits & kMatMask];
+          const V3 e = mat_emitted(m);
+          if (e.x != 0.0f || e.y != 0.0f || e.z != 0.0f) {
+            radiance = beta * e;
+            add = true;
+          }
+          const Uniforms4 u = philox_uniforms(rp.seed, pixel, sample, bounce, 0u);
+          Ray sc_ray;
+          V3 att;
+          if (mat_scatter(m, ray_d, v3(h0.x, h0.y, h0.z), v3(h1.x, h1.y, h1.z), (bits & kFrontBit) != 0u, u.u, sc_ray, att)) {
+            // trace_ray(scattered, depth - 1): depth 0 returns black (renderer.rs:20-22)
+            if (bounce + 1u < (uint32_t)rp.max_depth) {
+              alive = true;
+              const V3 nbeta = beta * att;
+              no = make_float4(sc_ray.o.x, sc_ray.o.y, sc_ray.o.z, o4.w);
+              nd = make_float4(sc_ray.d.x, sc_ray.d.y, sc_ray.d.z, d4.w);
+              nb = make_float4(nbeta.x, nbeta.y, nbeta.z, u2f(bounce + 1u));
+            }
           }
         }
+        if (add) {
+          float *px = accum + (size_t)pixel * 3;
+          atomicAdd(px + 0, radiance.x);
+          atomicAdd(px + 1, radiance.y);
+          atomicAdd(px + 2, radiance.z);
+        }
       }
-      if (add) {
-        float *px = accum + (size_t)pixel * 3;
-        atomicAdd(px + 0, radiance.x);
-        atomicAdd(px + 1, radiance.y);
-        atomicAdd(px + 2, radiance.z);
+      // survivors: one shared-memory atomic per warp, no barrier
+      const uint32_t amask = __ballot_sync(0xffffffffu, alive);
+      if (amask != 0u) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&s_w, (uint32_t)__popc(amask));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (alive) {
+          const uint32_t slot = seg_base + base + (uint32_t)__popc(amask & lt_mask);
+          b.nray_o[slot] = no;
+          b.nray_d[slot] = nd;
+          b.nbeta[slot] = nb;
+        }
       }
     }
-    uint32_t total;
-    const uint32_t off = block_rank(alive, s_warp, &total);  // two barriers: stage `buf`, s_perm, s_cnt, s_off are free after it
-    if (alive) {
-      const uint32_t slot = seg_base + w + off;
-      b.ray_o[slot] = no;
-      b.ray_d[slot] = nd;
-      b.beta[slot] = nb;
-    }
-    w += total;
-    __syncthreads();  // s_warp is reused by the next block_rank
+    // no barrier here: the next window's pass 1 touches only the other histogram, and s_perm is rewritten after its
+    // first barrier, which every thread reaches only after it has finished this loop
   }
+  __syncthreads();
+  uint32_t w = s_w;  // survivors written so far = write cursor inside the segment (same value in every thread)
 
   // ---- regeneration: top the segment up with fresh camera paths.  Path index -> (sample, 32-pixel row of one of this
   // rank's 32x32 tiles, lane): a warp starts 32 horizontally adjacent pixels of one sample (coherent primary rays,
@@ -561,9 +537,9 @@ __device__ __forceinline__ uint32_t stage_shade(uint32_t seg, uint32_t half, Ctl
         const float u = ((float)x + jit.u[0]) / (float)rp.width;   // renderer.rs:96
         const float v = ((float)y + jit.u[1]) / (float)rp.height;  // renderer.rs:97
         const Ray ray = camera_get_ray(rp.cam, u, v);
-        b.ray_o[slot] = make_float4(ray.o.x, ray.o.y, ray.o.z, u2f(pixel));
-        b.ray_d[slot] = make_float4(ray.d.x, ray.d.y, ray.d.z, u2f(sample));
-        b.beta[slot] = make_float4(1.0f, 1.0f, 1.0f, u2f(0u));
+        b.nray_o[slot] = make_float4(ray.o.x, ray.o.y, ray.o.z, u2f(pixel));
+        b.nray_d[slot] = make_float4(ray.d.x, ray.d.y, ray.d.z, u2f(sample));
+        b.nbeta[slot] = make_float4(1.0f, 1.0f, 1.0f, u2f(0u));
       }
       w += total;
       __syncthreads();
@@ -583,7 +559,7 @@ __device__ __forceinline__ uint32_t stage_shade(uint32_t seg, uint32_t half, Ctl
 // ---- per-stage kernels: one block per segment --------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock, kSegPerSM) k_extend_pre(Ctl *ctl, SegRange sr, DScene sc, ExtendOut out, TaskQ tq, float t_min,
                                                                   float t_max) {
-  if (blockIdx.x == 0 && threadIdx.x == 0) {  // iteration bookkeeping (this half's previous shade has finished: stream order)
+  if (blockIdx.x == 0 && threadIdx.x == 0) {  // iteration bookkeeping (the previous shade has finished: stream order)
     const uint32_t live = ctl->n_live[sr.half];
     if (live) {
       atomicAdd(&ctl->rays, (unsigned long long)live);
@@ -602,58 +578,10 @@ __global__ void __launch_bounds__(kBlock, kSegPerSM) k_extend_post(SegRange sr, 
                                                                    float t_max) {
   stage_post(sr.seg0 + blockIdx.x, sr.n_seg, sc, out, tq, round, t_min, t_max);
 }
-
-__device__ __forceinline__ float4 *shade_smem_setup(uint8_t *s_dyn, uint64_t *s_bar) {
-  if (threadIdx.x == 0) {
-    mbar_init(&s_bar[0], 1);
-    mbar_init(&s_bar[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  return reinterpret_cast<float4 *>((reinterpret_cast<uintptr_t>(s_dyn) + 127) & ~(uintptr_t)127);
-}
 __global__ void __launch_bounds__(kBlock, kSegPerSM) k_shade(Ctl *ctl, SegRange sr, DScene sc, RenderParams rp, Buffers b, float *accum) {
-  extern __shared__ uint8_t s_dyn[];
-  __shared__ __align__(8) uint64_t s_bar[2];
-  float4 *s_raw = shade_smem_setup(s_dyn, s_bar);
-  uint32_t used[2] = {0u, 0u};
-  stage_shade(sr.seg0 + blockIdx.x, sr.half, ctl, sc, rp, b, accum, s_raw, s_bar, used);
+  stage_shade(sr.seg0 + blockIdx.x, sr.half, ctl, sc, rp, b, accum);
 }
 
-// ---- the production path: ONE persistent kernel.  Segments never interact (the only shared state is the path counter
-// and the film), so a block simply loops over the stages of its own segment until the segment is empty and the path
-// supply exhausted: no kernel boundaries, no grid-wide barriers, no host polling, and blocks in different stages overlap
-// on an SM (the ALU-bound traversal of one block fills the issue slots the latency-bound shading of another leaves).
-__global__ void __launch_bounds__(kBlock, kSegPerSM) k_wavefront(Ctl *ctl, DScene sc, RenderParams rp, Buffers b, TaskQ tq, int rounds,
-                                                                 float *accum, uint32_t refill_lanes) {
-  extern __shared__ uint8_t s_dyn[];
-  __shared__ __align__(8) uint64_t s_bar[2];
-  float4 *s_raw = shade_smem_setup(s_dyn, s_bar);
-  const uint32_t seg = blockIdx.x, n_seg = gridDim.x;
-  const ExtendOut out{b, nullptr};
-  uint32_t used[2] = {0u, 0u};
-  unsigned long long my_rays = 0;
-  uint32_t my_iters = 0;
-  uint32_t n = stage_shade(seg, 0u, ctl, sc, rp, b, accum, s_raw, s_bar, used);  // empty segment: pure regeneration
-  while (n > 0) {
-    my_rays += n;
-    my_iters++;
-    __syncthreads();
-    stage_pre(seg, n_seg, sc, out, tq, kEps, INFINITY);  // renderer.rs:24: (EPSILON, +inf)
-    for (int r = 0; r < rounds; r++) {
-      __syncthreads();
-      stage_traverse<false>(seg, n_seg, ctl, sc, tq, r, kEps, b.cap, refill_lanes);
-      __syncthreads();
-      stage_post(seg, n_seg, sc, out, tq, r, kEps, INFINITY);
-    }
-    __syncthreads();
-    n = stage_shade(seg, 0u, ctl, sc, rp, b, accum, s_raw, s_bar, used);
-  }
-  if (threadIdx.x == 0) {
-    atomicAdd(&ctl->rays, my_rays);
-    atomicMax(&ctl->iterations[0], my_iters);
-  }
-}
 
 // out = rgb * scale (renderer.rs:103)
 __global__ void k_scale(const float *in, float *out, size_t n, float scale) {

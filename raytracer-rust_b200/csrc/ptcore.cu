@@ -70,6 +70,7 @@ struct Workspace {
   uint32_t segments = 0, cap = 0;
   int rounds = 0;
   DevBuf<float4> ray_o, ray_d, beta, hit0, hit1;
+  DevBuf<float4> ray_o2, ray_d2, beta2;  // second set of ray arrays (renders only): k_shade reads one set, writes the other
   DevBuf<uint32_t> cnt;
   DevBuf<uint2> tq_ray[2];
   DevBuf<float4> tq_o[2], tq_d[2];
@@ -79,8 +80,10 @@ struct Workspace {
 
   size_t slots() const { return (size_t)segments * cap; }
   // grow-only in cap; segments and rounds are fixed per scene / device
-  void ensure(uint32_t seg, uint32_t want_cap, int mesh_rounds, bool want_ids) {
-    if (seg == segments && want_cap <= cap && mesh_rounds == rounds && (!want_ids || ids.n >= slots())) return;
+  void ensure(uint32_t seg, uint32_t want_cap, int mesh_rounds, bool want_ids, bool want_pingpong) {
+    if (seg == segments && want_cap <= cap && mesh_rounds == rounds && (!want_ids || ids.n >= slots()) &&
+        (!want_pingpong || ray_o2.n >= slots()))
+      return;
     segments = seg;
     cap = std::max(cap, want_cap);
     rounds = mesh_rounds;
@@ -92,8 +95,13 @@ struct Workspace {
       tq_cnt.alloc((size_t)(rounds + 1) * segments);
     }
     if (want_ids) ids.alloc(n);
+    if (want_pingpong) ray_o2.alloc(n), ray_d2.alloc(n), beta2.alloc(n);
   }
-  Buffers buffers() const { return Buffers{ray_o.p, ray_d.p, beta.p, hit0.p, hit1.p, cnt.p, cap}; }
+  // flip = 0: the stages read set 1 and k_shade writes set 2; flip = 1: the other way round
+  Buffers buffers(int flip = 0) const {
+    if (flip == 0) return Buffers{ray_o.p, ray_d.p, beta.p, hit0.p, hit1.p, cnt.p, cap, ray_o2.p, ray_d2.p, beta2.p};
+    return Buffers{ray_o2.p, ray_d2.p, beta2.p, hit0.p, hit1.p, cnt.p, cap, ray_o.p, ray_d.p, beta.p};
+  }
   TaskQ taskq() const {
     TaskQ q;
     for (int k = 0; k < 2; k++) q.ray[k] = tq_ray[k].p, q.o[k] = tq_o[k].p, q.d[k] = tq_d[k].p, q.res[k] = tq_res[k].p;
@@ -127,8 +135,6 @@ struct ptc_scene {
   static constexpr int kRing = 4;
   cudaEvent_t ring_ev[kRing] = {nullptr, nullptr, nullptr, nullptr};
   cudaStream_t own_stream = nullptr;
-  cudaStream_t aux_stream = nullptr;  // second half-wavefront
-  cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
   std::vector<cudaEvent_t> timing_events;
 
   uint32_t segments() const { return (uint32_t)(sm_count * kSegPerSM); }
@@ -140,9 +146,6 @@ struct ptc_scene {
       if (e) cudaEventDestroy(e);
     for (auto &e : timing_events) cudaEventDestroy(e);
     if (own_stream) cudaStreamDestroy(own_stream);
-    if (aux_stream) cudaStreamDestroy(aux_stream);
-    if (fork_ev) cudaEventDestroy(fork_ev);
-    if (join_ev) cudaEventDestroy(join_ev);
   }
 };
 
@@ -203,9 +206,9 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
   cap64 = std::max<uint64_t>((cap64 + kBlock - 1) / kBlock * kBlock, kBlock);
   if (cap64 * segments > 0x7fffffffull) throw std::invalid_argument("pool_paths too large");
   ensure_ctl(s);
-  s->ws.ensure(segments, (uint32_t)cap64, s->mesh_objects, false);
-  Buffers b = s->ws.buffers();
-  b.cap = (uint32_t)cap64;  // a pool smaller than the allocation simply uses a smaller segment stride
+  s->ws.ensure(segments, (uint32_t)cap64, s->mesh_objects, false, true);
+  Buffers bufs[2] = {s->ws.buffers(0), s->ws.buffers(1)};
+  bufs[0].cap = bufs[1].cap = (uint32_t)cap64;  // a pool smaller than the allocation simply uses a smaller segment stride
   const TaskQ tq = s->ws.taskq();
 
   RenderParams rp;
@@ -246,7 +249,7 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
   memset(&init, 0, sizeof(init));
   init.total_paths = rp.max_depth > 0 ? (unsigned long long)rp.n_my_tiles * 1024ull * (unsigned long long)rp.n_samples : 0ull;
   CK(cudaMemcpyAsync(s->d_ctl.p, &init, sizeof(Ctl), cudaMemcpyHostToDevice, stream));
-  CK(cudaMemsetAsync(b.cnt, 0, segments * sizeof(uint32_t), stream));
+  CK(cudaMemsetAsync(bufs[0].cnt, 0, segments * sizeof(uint32_t), stream));
 
   const bool counters = (st->flags & PTC_FLAG_COUNTERS) != 0;
   const bool timing = (st->flags & PTC_FLAG_TIMING) != 0;
@@ -272,67 +275,45 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
 
   CK(cudaEventRecord(ev_begin, stream));
   uint64_t launches = 0;
-  static const bool persistent = getenv("PTC_PERSISTENT") != nullptr;  // measured dead end, kept for the record
-  static const bool two_streams = getenv("PTC_TWO_STREAMS") != nullptr;  // measured: no gain, kept as a knob
   static const uint32_t refill = getenv("PTC_REFILL") ? (uint32_t)atoi(getenv("PTC_REFILL")) : kRefillLanes;
-  auto is_done = [](const Ctl &c) { return c.n_live[0] == 0 && c.n_live[1] == 0 && c.next_path >= c.total_paths; };
-  if (persistent && !timing && !counters) {
-    k_wavefront<<<segments, kBlock, kShadeSmem, stream>>>(s->d_ctl.p, s->ds, rp, b, tq, rounds, d_accum, refill);
-    launches = 1;
-  } else if (init.total_paths != 0) {
-    // Optionally two half-wavefronts on two streams, so that the kernel tails of one half could be filled by the other;
-    // measured on B200 this does not beat a single stream, so it is off unless asked for.
-    const int halves = (two_streams && !timing && segments >= 2) ? 2 : 1;
-    cudaStream_t hs[2] = {stream, s->aux_stream};
-    SegRange sr[2];
-    uint32_t blocks[2];
-    blocks[0] = halves == 2 ? segments / 2 : segments;
-    blocks[1] = segments - blocks[0];
-    sr[0] = SegRange{0u, segments, 0u};
-    sr[1] = SegRange{blocks[0], segments, 1u};
-    if (halves == 2) {  // the second stream starts after the control block and the counts are reset
-      CK(cudaEventRecord(s->fork_ev, stream));
-      CK(cudaStreamWaitEvent(hs[1], s->fork_ev, 0));
-    }
-    auto run_extend = [&](int h) {
-      const ExtendOut eo{b, nullptr};
+  auto is_done = [](const Ctl &c) { return c.n_live[0] == 0 && c.next_path >= c.total_paths; };
+  if (init.total_paths != 0) {
+    const SegRange sr{0u, segments, 0u};
+    int flip = 0;  // the ray set the extend stages read
+    auto run_extend = [&]() {
+      const ExtendOut eo{bufs[flip], nullptr};
       if (timing) mark(ST_PRE);
-      k_extend_pre<<<blocks[h], kBlock, 0, hs[h]>>>(s->d_ctl.p, sr[h], s->ds, eo, tq, kEps, INFINITY);  // renderer.rs:24
+      k_extend_pre<<<segments, kBlock, 0, stream>>>(s->d_ctl.p, sr, s->ds, eo, tq, kEps, INFINITY);  // renderer.rs:24
       for (int r = 0; r < rounds; r++) {
         if (timing) mark(ST_TRAVERSE);
-        if (counters) k_traverse<true><<<blocks[h], kBlock, 0, hs[h]>>>(s->d_ctl.p, sr[h], s->ds, tq, r, kEps, b.cap, refill);
-        else k_traverse<false><<<blocks[h], kBlock, 0, hs[h]>>>(s->d_ctl.p, sr[h], s->ds, tq, r, kEps, b.cap, refill);
+        if (counters) k_traverse<true><<<segments, kBlock, 0, stream>>>(s->d_ctl.p, sr, s->ds, tq, r, kEps, eo.b.cap, refill);
+        else k_traverse<false><<<segments, kBlock, 0, stream>>>(s->d_ctl.p, sr, s->ds, tq, r, kEps, eo.b.cap, refill);
         if (timing) mark(ST_POST);
-        k_extend_post<<<blocks[h], kBlock, 0, hs[h]>>>(sr[h], s->ds, eo, tq, r, kEps, INFINITY);
+        k_extend_post<<<segments, kBlock, 0, stream>>>(sr, s->ds, eo, tq, r, kEps, INFINITY);
       }
       launches += 1 + 2 * (uint64_t)rounds;
     };
-    auto run_shade = [&](int h) {
+    auto run_shade = [&]() {  // reads set `flip`, writes the other one, which the next extend then reads
       if (timing) mark(ST_SHADE);
-      k_shade<<<blocks[h], kBlock, kShadeSmem, hs[h]>>>(s->d_ctl.p, sr[h], s->ds, rp, b, d_accum);
+      k_shade<<<segments, kBlock, 0, stream>>>(s->d_ctl.p, sr, s->ds, rp, bufs[flip], d_accum);
       launches += 1;
+      flip ^= 1;
     };
-    for (int h = 0; h < halves; h++) run_shade(h);  // initial fill: a shade pass over empty segments is pure regeneration
+    run_shade();  // initial fill: a shade pass over empty segments is pure regeneration
     std::deque<int> pending;
     int ring_next = 0;
     uint64_t it = 0;
     const int check_every = 4;
     bool finished = false;
     while (!finished) {
-      for (int h = 0; h < halves; h++) {
-        run_extend(h);
-        run_shade(h);
-      }
+      run_extend();
+      run_shade();
       it++;
       if (it % check_every == 0) {
-        // snapshot the control block (after both halves' work so far); consume finished snapshots without stalling the
-        // launch queue.  The host only blocks when the ring is full.
+        // snapshot the control block; consume finished snapshots without stalling the launch queue.  The host only
+        // blocks when the ring is full.
         const int k = ring_next;
         ring_next = (ring_next + 1) % ptc_scene::kRing;
-        if (halves == 2) {
-          CK(cudaEventRecord(s->join_ev, hs[1]));
-          CK(cudaStreamWaitEvent(stream, s->join_ev, 0));
-        }
         CK(cudaMemcpyAsync(&s->h_ctl[k], s->d_ctl.p, sizeof(Ctl), cudaMemcpyDeviceToHost, stream));
         CK(cudaEventRecord(s->ring_ev[k], stream));
         pending.push_back(k);
@@ -352,22 +333,18 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
         }
       }
     }
-    if (halves == 2) {  // join before the end-of-render event
-      CK(cudaEventRecord(s->join_ev, hs[1]));
-      CK(cudaStreamWaitEvent(stream, s->join_ev, 0));
-    }
   }
   CK(cudaGetLastError());
   CK(cudaEventRecord(ev_end, stream));
   CK(cudaMemcpyAsync(&s->h_ctl[0], s->d_ctl.p, sizeof(Ctl), cudaMemcpyDeviceToHost, stream));
   CK(cudaStreamSynchronize(stream));
   const Ctl fin = s->h_ctl[0];
-  if (!(fin.next_path >= fin.total_paths) || (!persistent && !is_done(fin))) throw std::runtime_error("wavefront loop ended before all paths terminated");
+  if (!is_done(fin)) throw std::runtime_error("wavefront loop ended before all paths terminated");
   if (stats) {
     memset(stats, 0, sizeof(*stats));
     stats->paths = rp.max_depth > 0 ? my_pixels * (uint64_t)rp.n_samples : 0;
     stats->rays = fin.rays;
-    stats->iterations = std::max(fin.iterations[0], fin.iterations[1]);
+    stats->iterations = fin.iterations[0];
     stats->kernel_launches = launches;
     float ms = 0.0f;
     CK(cudaEventElapsedTime(&ms, ev_begin, ev_end));
@@ -546,9 +523,6 @@ int ptc_scene_commit(ptc_scene *s, int device) {
   for (const DObject &o : s->hs.objects)
     if (o.type == OBJ_MESH) s->mesh_objects++;
   CK(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
-  CK(cudaStreamCreateWithFlags(&s->aux_stream, cudaStreamNonBlocking));
-  CK(cudaEventCreateWithFlags(&s->fork_ev, cudaEventDisableTiming));
-  CK(cudaEventCreateWithFlags(&s->join_ev, cudaEventDisableTiming));
   s->committed = true;
   return 0;
   PTC_GUARD_END
@@ -652,7 +626,7 @@ int ptc_intersect(ptc_scene *s, const float *origins, const float *dirs, int64_t
   // the rays are laid out like a render's pool (segment b = slots [b * cap, ...)) and go through the SAME kernels
   const uint32_t segments = s->segments();
   const uint32_t cap = (uint32_t)(((uint64_t)n + segments - 1) / segments + kBlock - 1) / kBlock * kBlock;
-  s->ws_hook.ensure(segments, cap, s->mesh_objects, true);
+  s->ws_hook.ensure(segments, cap, s->mesh_objects, true, false);
   Buffers b = s->ws_hook.buffers();
   b.cap = cap;
   const TaskQ tq = s->ws_hook.taskq();

@@ -88,6 +88,9 @@ int sim_scene_commit(sim_scene *s, int /*device*/) {
   }
 }
 
+// for tests/hostsim/wfsim.cpp (the SIMT cost model)
+const DScene *sim_scene_dscene(const sim_scene *s) { return s->committed ? &s->ds : nullptr; }
+
 int sim_scene_mesh_info(const sim_scene *s, int object, ptc_mesh_info *info, uint8_t *dead, int32_t *order) {
   if (object < 0 || (size_t)object >= s->hs.objects.size() || s->hs.objects[object].type != OBJ_MESH) return -1;
   const MeshBuild &m = *s->hs.meshes[s->hs.objects[object].mesh];
