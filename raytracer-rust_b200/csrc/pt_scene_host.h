@@ -112,6 +112,8 @@ struct HostScene {
       if (!m->built) build_mesh(*m);
     for (auto &m : meshes)
       if (m->wide_depth + 2 > kTraversalStack) throw std::runtime_error("wide BVH deeper than the traversal stack");
+    if (materials.size() > (size_t)1 << 26) throw std::runtime_error("more than 2^26 materials");
+    for (DObject &o : objects) o.mat_type = materials[(size_t)o.material].type;
   }
 };
 

@@ -17,7 +17,7 @@ struct alignas(16) DObject {
   int32_t type;
   int32_t material;
   int32_t mesh;
-  int32_t pad;
+  int32_t mat_type;  // DMaterial::type of `material`, filled at commit: the shade stage's sort key rides in the hit record
   float f[32];
 };
 static_assert(sizeof(DObject) == 144, "DObject layout");

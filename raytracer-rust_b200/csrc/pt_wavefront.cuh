@@ -92,11 +92,13 @@ struct TaskQ {
   uint32_t *cnt;   // [(rounds + 1) * S]
 };
 
-constexpr uint32_t kHitBit = 0x80000000u, kFrontBit = 0x40000000u, kMatMask = 0x3fffffffu;
+// hit1.w: hit << 31 | front_face << 30 | material type << 26 (the shade stage's sort key) | material index
+constexpr uint32_t kHitBit = 0x80000000u, kFrontBit = 0x40000000u, kMatMask = 0x03ffffffu;
+constexpr int kTypeShift = 26;
 
 __device__ __forceinline__ void write_hit(const ExtendOut &out, uint32_t i, const Hit &h) {
   out.b.hit0[i] = make_float4(h.px, h.py, h.pz, h.t);
-  out.b.hit1[i] = make_float4(h.nx, h.ny, h.nz, u2f(kHitBit | (h.front_face ? kFrontBit : 0u) | ((uint32_t)h.material & kMatMask)));
+  out.b.hit1[i] = make_float4(h.nx, h.ny, h.nz, u2f(kHitBit | (h.front_face ? kFrontBit : 0u) | ((uint32_t)h.material & ~(kHitBit | kFrontBit))));
   if (out.ids) out.ids[i] = make_int2(h.object, h.triangle);
 }
 __device__ __forceinline__ void write_miss(const ExtendOut &out, uint32_t i) {
@@ -131,7 +133,7 @@ __device__ __forceinline__ int scan_objects(const DScene &sc, const DObject *obj
       closest = tmp.t;
       best = tmp;
       best.object = k;
-      best.material = ob->material;
+      best.material = ob->material | (ob->mat_type << kTypeShift);  // index | type << 26, see write_hit
     }
   }
   return -1;
@@ -308,7 +310,7 @@ __device__ __forceinline__ void stage_post(uint32_t seg, uint32_t n_seg, const D
           closest = tmp.t;
           best = tmp;
           best.object = k;
-          best.material = ob->material;
+          best.material = ob->material | (ob->mat_type << kTypeShift);  // index | type << 26, see write_hit
         }
       }
       park = scan_objects(sc, objs, ray, t_min, closest, best, improved, k + 1, mr);
@@ -392,7 +394,7 @@ __device__ __forceinline__ uint32_t stage_shade(uint32_t seg, uint32_t half, Ctl
       uint32_t key = kShadeClasses - 1;
       if (idx < wn) {
         const uint32_t bits = f2u(__ldg(&b.hit1[win_base + idx]).w);
-        key = (bits & kHitBit) ? 1u + (uint32_t)__ldg(&sc.materials[bits & kMatMask].type) : 0u;
+        key = (bits & kHitBit) ? 1u + ((bits >> kTypeShift) & 15u) : 0u;
       }
       const uint32_t peers = __match_any_sync(0xffffffffu, key);
       const int leader = __ffs((int)peers) - 1;
