@@ -151,12 +151,12 @@ PT_HD bool mesh_root_may_hit(const DMesh &mesh, const MeshRay &r, float t_min, f
 
 // Second half of Mesh::hit (mesh_object.rs:293-326): object-space closest triangle -> world-space HitRecord, with the
 // closed-interval recheck on the (quirky) world t.
-PT_HD bool mesh_finish(const float *f, const DMesh &mesh, const Ray &ray, const MeshRay &mr, const MeshHit &mh, float t_min,
-                       float t_max, Hit &h) {
+// `nq` = mesh.normals[mh.tri], loaded by the caller (k_extend_post issues it together with its other gathers).
+PT_HD bool mesh_finish(const float *f, float4 nq, const Ray &ray, const MeshRay &mr, const MeshHit &mh, float t_min, float t_max,
+                       Hit &h) {
   const M4 w2o = load_m4(f), o2w = load_m4(f + 16);
   const V3 o = mr.o, d = mr.d;
   const V3 p_obj = o + d * mh.t;  // ray.at(t), bvh.rs:119
-  const float4 nq = ldg4(mesh.normals + mh.tri);
   V3 n_obj = v3(nq.x, nq.y, nq.z);
   if (!(dot(d, n_obj) < 0.0f)) n_obj = -n_obj;  // bvh.rs:120-126
   const V3 pw = mat_point(o2w, p_obj);
@@ -168,6 +168,11 @@ PT_HD bool mesh_finish(const float *f, const DMesh &mesh, const Ray &ray, const 
   set_pos(h, pw);
   set_face_normal(h, ray.d, nw);
   return true;
+}
+
+PT_HD bool mesh_finish(const float *f, const DMesh &mesh, const Ray &ray, const MeshRay &mr, const MeshHit &mh, float t_min,
+                       float t_max, Hit &h) {
+  return mesh_finish(f, ldg4(mesh.normals + mh.tri), ray, mr, mh, t_min, t_max, h);
 }
 
 // src/mesh/mesh_object.rs:262-329, straight line (parity hooks and the hostsim harness; the renderer splits it into

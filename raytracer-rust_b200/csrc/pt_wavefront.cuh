@@ -291,21 +291,25 @@ __device__ __forceinline__ void stage_post(uint32_t seg, uint32_t n_seg, const D
       const float2 res = tq.res[par][j];
       i = rk.x;
       const int k = (int)rk.y;
+      const DObject *ob = objs + k;
+      const uint32_t tri = f2u(res.y);
+      // the stage is bound by the latency of these gathers: issue all of them before the first use
       const float4 o4 = out.b.ray_o[i], d4 = out.b.ray_d[i];
+      const float h1w = out.b.hit1[i].w, h0w = out.b.hit0[i].w;
+      float4 nq = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      if (tri != 0xffffffffu) nq = ldg4(sc.meshes[ob->mesh].normals + tri);
       const Ray ray{v3(o4.x, o4.y, o4.z), v3(d4.x, d4.y, d4.z)};
-      const bool any = (f2u(out.b.hit1[i].w) & kHitBit) != 0u;
-      if (any) closest = out.b.hit0[i].w;  // == the t_max the traversal ran with
+      const bool any = (f2u(h1w) & kHitBit) != 0u;
+      if (any) closest = h0w;  // == the t_max the traversal ran with
       Hit best;
       best.triangle = -1;
       bool improved = false;
-      const uint32_t tri = f2u(res.y);
       if (tri != 0xffffffffu) {
-        const DObject *ob = objs + k;
         const MeshRay omr = mesh_object_ray(ob->f, ray);  // same inputs, same bits as in k_extend_pre
         MeshHit mh;
         mh.t = res.x, mh.tri = tri, mh.order = 0u;
         Hit tmp;
-        if (mesh_finish(ob->f, sc.meshes[ob->mesh], ray, omr, mh, t_min, closest, tmp)) {
+        if (mesh_finish(ob->f, nq, ray, omr, mh, t_min, closest, tmp)) {
           improved = true;
           closest = tmp.t;
           best = tmp;
@@ -368,7 +372,7 @@ __device__ __forceinline__ uint32_t block_rank(bool flag, uint32_t *s_warp /* [k
 //   * survivors are appended at a block-local cursor (one shared-memory atomic per warp) in the OTHER ray buffer:
 //     with gathers in flight all over the window, compaction in place would overwrite rays that are still to be read.
 // Returns the new ray count of the segment.
-__device__ __forceinline__ uint32_t stage_shade(uint32_t seg, uint32_t half, Ctl *ctl, const DScene &sc, const RenderParams &rp, const Buffers &b,
+__device__ __forceinline__ uint32_t stage_shade(uint32_t seg, uint32_t n_seg, uint32_t half, Ctl *ctl, const DScene &sc, const RenderParams &rp, const Buffers &b,
                                                 float *accum) {
   __shared__ uint16_t s_perm[kShadeWindow];
   __shared__ uint32_t s_hist[2][16];
@@ -501,8 +505,11 @@ __device__ __forceinline__ uint32_t stage_shade(uint32_t seg, uint32_t half, Ctl
   const unsigned long long per_sample = (unsigned long long)rp.n_my_tiles * 1024ull;
   for (;;) {
     if (tid == 0) {
-      const uint32_t free_slots = b.cap - w;
       const unsigned long long total = ctl->total_paths;
+      // no more than a fair share of the whole job per block, in whole 32-pixel rows: a render smaller than the pool
+      // would otherwise be swallowed by the first few segments and traced by that many blocks
+      const unsigned long long share = ((total + n_seg - 1) / n_seg + 31ull) & ~31ull;
+      const uint32_t free_slots = (uint32_t)min((unsigned long long)(b.cap - w), share);
       unsigned long long first = total;
       if (free_slots > 0 && ctl->next_path < total) first = atomicAdd(&ctl->next_path, (unsigned long long)free_slots);
       s_first = first;
@@ -581,7 +588,7 @@ __global__ void __launch_bounds__(kBlock, kSegPerSM) k_extend_post(SegRange sr, 
   stage_post(sr.seg0 + blockIdx.x, sr.n_seg, sc, out, tq, round, t_min, t_max);
 }
 __global__ void __launch_bounds__(kBlock, kSegPerSM) k_shade(Ctl *ctl, SegRange sr, DScene sc, RenderParams rp, Buffers b, float *accum) {
-  stage_shade(sr.seg0 + blockIdx.x, sr.half, ctl, sc, rp, b, accum);
+  stage_shade(sr.seg0 + blockIdx.x, sr.n_seg, sr.half, ctl, sc, rp, b, accum);
 }
 
 
