@@ -37,6 +37,15 @@ WORKLOAD = "C2 semesterbild.json 800x600, 256 spp, max_bounces 30 (3 cubes, 4748
 METRIC = "Mpaths/s (semesterbild 800x600x256spp, depth 30)"
 
 
+def measured_traffic():
+    """DRAM bytes per extend ray from the committed ncu capture (dram__bytes_read.sum + dram__bytes_write.sum of the three
+    extend kernels of one full-pool iteration, profiles/r1_extend_traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "r1_extend_traffic.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["dram_bytes_per_ray"])
+    return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -293,6 +302,7 @@ def main():
     fp32_peak = sms * 128 * sm_mhz * 1e6 / 1e12  # T instr/s at the clock sampled under load
     achieved_tinstr = instr_per_ray * rays_rank / ext_s / 1e12 if ext_s > 0 else 0.0
 
+    dram_per_ray = measured_traffic()
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -312,7 +322,12 @@ def main():
                              "k_shade (incl. path regeneration)": shade_ms / render_ms,
                              "launch gaps": max(0.0, 1.0 - (ext_ms + shade_ms) / render_ms)},
             "roofline": {"kernel": "extend stage = k_extend_pre + k_traverse + k_extend_post (one logical kernel, timed together)", "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": peak_kind,
+                         "frac": achieved_gbs / hbm_peak,
+                         "traffic": dram_per_ray * rays_per_launch if dram_per_ray else None,
+                         "traffic_note": "bytes per launch of the stage: DRAM bytes per ray of the committed ncu capture "
+                                         "(profiles/r1_extend_traffic.json) x rays per launch; below the algorithmic bytes because "
+                                         "the BVH nodes and triangles are served from L1/L2",
+                         "algorithmic_bytes_per_launch": bytes_per_ray * rays_per_launch, "peak_source": peak_kind,
                          "algorithmic_bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray,
                          "rays_per_launch": rays_per_launch, "avg_launch_ms": ext_ms / max(1, ext_launches),
                          "extend_grays_per_s": rays_rank / ext_s / 1e9 if ext_s > 0 else 0.0,

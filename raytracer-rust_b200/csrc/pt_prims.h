@@ -84,7 +84,16 @@ PT_HD bool hit_quad(const float *f, const Ray &ray, float t_min, float t_max, Hi
 }
 
 // src/objects/cube.rs:59-158.  f[0..15] = world_to_object, f[16..31] = object_to_world.
-PT_HD bool hit_cube(const float *f, const Ray &ray, float t_min, float t_max, Hit &h) {
+//
+// Cube::hit in two halves.  Whether a cube hit is accepted depends on t_obj and t_world only; the normal (face pick,
+// normalize_or_zero, (M^-1)^T n, normalize, face flip: more than half of the instructions of an accepted hit) is a pure
+// function of the object-space hit point and is only ever read from the record that wins the list scan.  hit_cube_t
+// does the first half and leaves the object-space point in the record's normal fields with front_face =
+// kCubeNormalPending; cube_finish_normal completes the record.  The extend stage calls the second half once per ray,
+// after the scan, instead of once per accepted cube inside it (in C2 a warp of 32 incoherent rays used to run the full
+// hit path of all three cubes at ~10 active lanes each).  hit_cube = both halves back to back, same bits.
+constexpr int32_t kCubeNormalPending = 2;
+PT_HD bool hit_cube_t(const float *f, const Ray &ray, float t_min, float t_max, Hit &h) {
   const M4 w2o = load_m4(f);
   const V3 o = mat_point(w2o, ray.o);
   const V3 d = mat_vector(w2o, ray.d);  // not renormalised (cube.rs:70-83)
@@ -98,6 +107,19 @@ PT_HD bool hit_cube(const float *f, const Ray &ray, float t_min, float t_max, Hi
   const float t_obj = t_enter > 0.0f ? t_enter : t_exit;
   if (t_obj >= t_max || t_obj <= t_min || t_obj < kEps) return false;
   const V3 p = o + d * t_obj;
+  const M4 o2w = load_m4(f + 16);
+  const V3 pw = mat_point(o2w, p);
+  if (dot(pw - ray.o, ray.d) < 0.0f) return false;
+  const float t_world = dot(pw - ray.o, ray.d);
+  if (t_world < t_min || t_world > t_max) return false;  // closed interval (cube.rs:150)
+  h.t = t_world;
+  set_pos(h, pw);
+  h.nx = p.x, h.ny = p.y, h.nz = p.z;  // object-space hit point, for cube_finish_normal
+  h.front_face = kCubeNormalPending;
+  return true;
+}
+PT_HD void cube_finish_normal(const float *f, const Ray &ray, Hit &h) {
+  const V3 p = v3(h.nx, h.ny, h.nz);
   V3 n = v3(0, 0, 0);
   const float ax = fabsf(p.x), ay = fabsf(p.y), az = fabsf(p.z);
   const float tol = 1e-4f;
@@ -107,20 +129,21 @@ PT_HD bool hit_cube(const float *f, const Ray &ray, float t_min, float t_max, Hi
   else if (ax > ay && ax > az) n.x = signum(p.x);
   else if (ay > az) n.y = signum(p.y);
   else n.z = signum(p.z);
-  {  // glam normalize_or_zero
-    const float rcp = 1.0f / sqrtf(dot(n, n));
-    if (!isinf_f(rcp) && !isnan_f(rcp) && rcp > 0.0f) n = n * rcp;
-    else n = v3(0, 0, 0);
+  {  // glam normalize_or_zero.  n is +-1 on one axis unless p held a NaN: |n|^2 == 1 exactly, 1/sqrt(1) == 1, n * 1 == n
+    const float nn = dot(n, n);
+    if (nn != 1.0f) {
+      const float rcp = 1.0f / sqrtf(nn);
+      if (!isinf_f(rcp) && !isnan_f(rcp) && rcp > 0.0f) n = n * rcp;
+      else n = v3(0, 0, 0);
+    }
   }
-  const M4 o2w = load_m4(f + 16);
-  const V3 pw = mat_point(o2w, p);
+  const M4 w2o = load_m4(f);
   const V3 nw = normalized(mat_t_vector(w2o, n));
-  if (dot(pw - ray.o, ray.d) < 0.0f) return false;
-  const float t_world = dot(pw - ray.o, ray.d);
-  if (t_world < t_min || t_world > t_max) return false;  // closed interval (cube.rs:150)
-  h.t = t_world;
-  set_pos(h, pw);
   set_face_normal(h, ray.d, nw);
+}
+PT_HD bool hit_cube(const float *f, const Ray &ray, float t_min, float t_max, Hit &h) {
+  if (!hit_cube_t(f, ray, t_min, t_max, h)) return false;
+  cube_finish_normal(f, ray, h);
   return true;
 }
 

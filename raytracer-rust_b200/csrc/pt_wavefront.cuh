@@ -126,7 +126,7 @@ __device__ __forceinline__ int scan_objects(const DScene &sc, const DObject *obj
     }
     if (type == OBJ_SPHERE) hit = hit_sphere(ob->f, ray, t_min, closest, tmp);
     else if (type == OBJ_QUAD) hit = hit_quad(ob->f, ray, t_min, closest, tmp);
-    else if (type == OBJ_CUBE) hit = hit_cube(ob->f, ray, t_min, closest, tmp);
+    else if (type == OBJ_CUBE) hit = hit_cube_t(ob->f, ray, t_min, closest, tmp);  // normal: finish_hit, once per ray
     else hit = hit_plane(ob->f, ray, t_min, closest, tmp);
     if (hit) {
       improved = true;
@@ -137,6 +137,11 @@ __device__ __forceinline__ int scan_objects(const DScene &sc, const DObject *obj
     }
   }
   return -1;
+}
+
+// Completes the record that won the scan (pt_prims.h: a cube hit carries its normal as "pending" through the scan).
+__device__ __forceinline__ void finish_hit(const DObject *objs, const Ray &ray, Hit &best) {
+  if (best.front_face == kCubeNormalPending) cube_finish_normal(objs[best.object].f, ray, best);
 }
 
 // The object table is read by every lane for every ray; ray data streaming through L1 kept evicting it (the load of
@@ -191,6 +196,7 @@ __device__ __forceinline__ void stage_pre(uint32_t seg, uint32_t n_seg, const DS
       Hit best;
       bool improved = false;
       park = scan_objects(sc, objs, ray, t_min, closest, best, improved, 0, mr);  // renderer.rs:24
+      if (improved) finish_hit(objs, ray, best);
       if (improved) write_hit(out, i, best);
       else write_miss(out, i);
     }
@@ -318,6 +324,7 @@ __device__ __forceinline__ void stage_post(uint32_t seg, uint32_t n_seg, const D
         }
       }
       park = scan_objects(sc, objs, ray, t_min, closest, best, improved, k + 1, mr);
+      if (improved) finish_hit(objs, ray, best);
       if (improved) write_hit(out, i, best);  // otherwise the record parked by the previous stage stands
     }
     park_tasks(&s_ntask, tq, par ^ 1, seg_base, park, i, mr, closest);
