@@ -115,8 +115,6 @@ __device__ __forceinline__ int scan_objects(const DScene &sc, const DObject *obj
   for (int k = k_begin; k < sc.n_objects; k++) {
     const DObject *ob = objs + k;
     const int type = ob->type;
-    Hit tmp;
-    tmp.triangle = -1;
     bool hit;
     if (type == OBJ_MESH) {
       const MeshRay mr = mesh_object_ray(ob->f, ray);
@@ -124,15 +122,16 @@ __device__ __forceinline__ int scan_objects(const DScene &sc, const DObject *obj
       park_ray = mr;
       return k;
     }
-    if (type == OBJ_SPHERE) hit = hit_sphere(ob->f, ray, t_min, closest, tmp);
-    else if (type == OBJ_QUAD) hit = hit_quad(ob->f, ray, t_min, closest, tmp);
-    else if (type == OBJ_CUBE) hit = hit_cube_t(ob->f, ray, t_min, closest, tmp);  // normal: finish_hit, once per ray
-    else hit = hit_plane(ob->f, ray, t_min, closest, tmp);
+    // the primitives' tests write the record only when they accept the hit, so they can write straight into `best`
+    if (type == OBJ_SPHERE) hit = hit_sphere(ob->f, ray, t_min, closest, best);
+    else if (type == OBJ_QUAD) hit = hit_quad(ob->f, ray, t_min, closest, best);
+    else if (type == OBJ_CUBE) hit = hit_cube_t(ob->f, ray, t_min, closest, best);  // normal: finish_hit, once per ray
+    else hit = hit_plane(ob->f, ray, t_min, closest, best);
     if (hit) {
       improved = true;
-      closest = tmp.t;
-      best = tmp;
+      closest = best.t;
       best.object = k;
+      best.triangle = -1;
       best.material = ob->material | (ob->mat_type << kTypeShift);  // index | type << 26, see write_hit
     }
   }

@@ -121,6 +121,9 @@ def test_sharding_is_invisible(pt):
     # pool size and seed: the image must not depend on the pool, and must depend on the seed
     small, _ = cs.render(s.camera, s.render_settings(pool_paths=2048, **base))
     assert np.allclose(small, whole, rtol=1e-5, atol=1e-6)
+    # a pool far larger than the job: every block takes a fair share of the paths, not the first blocks everything
+    big, st_big = cs.render(s.camera, s.render_settings(pool_paths=1 << 21, **base))
+    assert np.allclose(big, whole, rtol=1e-5, atol=1e-6) and st_big.rays == st.rays
     other, _ = cs.render(s.camera, s.render_settings(**dict(base, seed=5)))
     assert not np.allclose(other, whole, rtol=1e-3, atol=1e-4)
 
