@@ -44,6 +44,14 @@ const char *pth_last_error(void);
 
 /* load_scene_from_json: returns NULL on error (message in pth_last_error), like the Err(..) of parser.rs:247. */
 pth_scene *pth_load_scene_from_json(const char *json_path);
+/* Extensions beyond the reference's loader, all OFF in pth_load_scene_from_json:
+ *   INFINITE_SPHERE_SKY  `"type": "infinite_sphere"` (not a variant of ObjectConfigVariant, parser.rs:136-165: the
+ *                        reference rejects the whole file, e.g. its own tungsten/teapot/scene.json) becomes the sky
+ *   WO3_STRIDE16         read .wo3 triangles with Tungsten's 16-byte records; without it the reader restates the
+ *                        reference's 12-byte mis-read (mesh_object.rs:188-190) index for index
+ *   SKIP_UNKNOWN         other unknown primitive types are skipped with a warning instead of failing the file */
+enum { PTH_LOAD_INFINITE_SPHERE_SKY = 1, PTH_LOAD_WO3_STRIDE16 = 2, PTH_LOAD_SKIP_UNKNOWN = 4 };
+pth_scene *pth_load_scene_from_json_ex(const char *json_path, int flags);
 /* An empty scene to be filled programmatically (tests, synthetic scenes). */
 pth_scene *pth_scene_new(void);
 void pth_scene_free(pth_scene *);

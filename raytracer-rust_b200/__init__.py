@@ -22,6 +22,7 @@ PTC_OK, PTC_E_INVALID, PTC_E_CUDA, PTC_E_NOMEM, PTC_E_STATE = 0, -1, -2, -3, -4
 MAT_LAMBERT, MAT_LAMBERT_CHECKER, MAT_METAL, MAT_DIELECTRIC, MAT_EMISSIVE, MAT_PLASTIC, MAT_ROUGH_CONDUCTOR, MAT_NULL = range(8)
 DIST_GGX, DIST_BECKMANN = 0, 1
 FLAG_COUNTERS, FLAG_TIMING = 1, 2
+LOAD_INFINITE_SPHERE_SKY, LOAD_WO3_STRIDE16, LOAD_SKIP_UNKNOWN = 1, 2, 4
 OBJ_SPHERE, OBJ_PLANE, OBJ_QUAD, OBJ_CUBE, OBJ_MESH = range(5)
 
 
@@ -161,6 +162,8 @@ def host():
     L.pth_last_error.restype = C.c_char_p
     L.pth_load_scene_from_json.argtypes = [C.c_char_p]
     L.pth_load_scene_from_json.restype = _vp
+    L.pth_load_scene_from_json_ex.argtypes = [C.c_char_p, C.c_int]
+    L.pth_load_scene_from_json_ex.restype = _vp
     L.pth_scene_new.restype = _vp
     L.pth_scene_free.argtypes = [_vp]
     L.pth_scene_free.restype = None
@@ -403,9 +406,10 @@ class Scene:
         return CoreScene(h)
 
 
-def load_scene_from_json(path):
-    """src/tungsten/parser.rs:245 — returns the host Scene (camera and render settings ride along)."""
-    h = host().pth_load_scene_from_json(os.fsencode(path))
+def load_scene_from_json(path, flags=0):
+    """src/tungsten/parser.rs:245 — returns the host Scene (camera and render settings ride along).  `flags` = LOAD_*
+    extensions of include/pthost.h (0 = the reference's behaviour, including its failures)."""
+    h = host().pth_load_scene_from_json_ex(os.fsencode(path), int(flags))
     if not h:
         raise RuntimeError(host().pth_last_error().decode())
     return Scene(h)

@@ -381,6 +381,66 @@ bool load_obj_triangles(const std::string &path, std::vector<float> &out, std::s
   return true;
 }
 
+// Mesh::from_wo3 (mesh_object.rs:141-259).  A Tungsten .wo3 file is: u64 vertex count, 32-byte vertices (position,
+// normal, uv), u64 triangle count, 16-byte triangles (v0, v1, v2: u32, material: i32).  The reference reads the
+// triangles as consecutive 12-byte index triples (it never skips the material word, mesh_object.rs:188-190), so from the
+// second record on its indices are taken from a shifted stream; triples with an index out of range are skipped
+// (:201-215), the rest become (wrong) triangles.  `tungsten_stride` = false restates exactly that; true reads the file
+// the way Tungsten wrote it (PTH_LOAD_WO3_STRIDE16).
+bool load_wo3_triangles(const std::string &path, std::vector<float> &out, std::string &err, bool tungsten_stride) {
+  std::ifstream f(path, std::ios::binary);
+  if (!f) {
+    err = "No such file or directory";
+    return false;
+  }
+  std::vector<unsigned char> buf((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+  size_t pos = 0;
+  auto rd_u64 = [&]() {
+    uint64_t v = 0;
+    memcpy(&v, &buf[pos], 8);
+    pos += 8;
+    return v;
+  };
+  if (buf.size() < 8) {
+    err = "failed to fill whole buffer";
+    return false;
+  }
+  const uint64_t nv = rd_u64();
+  if (nv > (buf.size() - pos) / 32) {
+    err = "failed to fill whole buffer";
+    return false;
+  }
+  std::vector<V> verts((size_t)nv);
+  for (uint64_t i = 0; i < nv; i++) {
+    float q[3];
+    memcpy(q, &buf[pos], 12);
+    verts[(size_t)i] = V{q[0], q[1], q[2]};
+    pos += 32;
+  }
+  if (buf.size() - pos < 8) {
+    err = "failed to fill whole buffer";
+    return false;
+  }
+  const uint64_t nt = rd_u64();
+  const size_t stride = tungsten_stride ? 16 : 12;
+  if (nt > (buf.size() - pos) / stride) {
+    err = "failed to fill whole buffer";
+    return false;
+  }
+  for (uint64_t i = 0; i < nt; i++) {
+    uint32_t idx[3];
+    memcpy(idx, &buf[pos], 12);
+    pos += stride;
+    if (idx[0] >= nv || idx[1] >= nv || idx[2] >= nv) continue;
+    push_triangle(out, verts[idx[0]], verts[idx[1]], verts[idx[2]]);
+  }
+  if (out.empty()) {
+    err = "[WO3_LOADER] No valid triangles in " + path;
+    return false;
+  }
+  return true;
+}
+
 // Radiance .hdr (RGBE) -> linear f32 RGB, the job of image::open(..).into_rgb32f() (parser.rs:502-506; image 0.25.6
 // is not vendored: parity unpinned).  Handles flat and new-style RLE scanlines, -Y +X orientation.
 bool load_hdr(const std::string &path, std::vector<float> &rgb, int &w, int &h, std::string &err) {
@@ -544,7 +604,7 @@ ptc_material plane_inline_material(const pth::Json &j) {
   throw std::runtime_error("plane.material: unknown variant `" + tag + "`");
 }
 
-pth_scene *load_scene(const std::string &json_path) {
+pth_scene *load_scene(const std::string &json_path, int flags) {
   std::ifstream f(json_path);
   if (!f) throw std::runtime_error("No such file or directory: " + json_path);
   std::stringstream ss;
@@ -743,14 +803,14 @@ pth_scene *load_scene(const std::string &json_path) {
       const std::string bsdf = need_bsdf();
       const int mat = find_or_magenta(s.get(), bsdfs, bsdf, "Mesh");
       const std::string path = scene_dir + "/" + file->str;
-      if (ends_with(file->str, ".wo3")) {
-        // Mesh::from_wo3 (mesh_object.rs:141-259) mis-reads Tungsten's 16-byte triangle records; out of scope here.
-        fprintf(stderr, "Error loading .wo3 mesh '%s': WO3 meshes are not supported by this host stand-in\n", path.c_str());
-        continue;
-      }
       std::vector<float> tris;
       std::string err;
-      if (!load_obj_triangles(path, tris, err)) {
+      if (ends_with(file->str, ".wo3")) {  // parser.rs:683-686
+        if (!load_wo3_triangles(path, tris, err, (flags & PTH_LOAD_WO3_STRIDE16) != 0)) {
+          fprintf(stderr, "Error loading .wo3 mesh '%s': %s\n", path.c_str(), err.c_str());  // object skipped, parser.rs:696-698
+          continue;
+        }
+      } else if (!load_obj_triangles(path, tris, err)) {
         fprintf(stderr, "Error loading .obj mesh '%s': %s\n", path.c_str(), err.c_str());  // object skipped, parser.rs:696-698
         continue;
       }
@@ -798,6 +858,24 @@ pth_scene *load_scene(const std::string &json_path) {
       pth_object o = obj_blank(PTH_CUBE, mat);
       transform_from(x.scale, x.rot, x.pos, o.o2w, o.w2o);  // Cube::new_transformed, cube.rs:20-29
       s->objects.push_back(o);
+    } else if (t == "infinite_sphere" && (flags & PTH_LOAD_INFINITE_SPHERE_SKY)) {
+      // Extension: Tungsten's environment light becomes the sky the renderer already knows how to look
+      // up (renderer.rs:38-63).  The primitive's rotation is ignored, like every orientation in that lookup.
+      const pth::Json *em = p.find("emission");
+      float c[3];
+      if (em && em->is_string() && ends_with(em->str, ".hdr")) {
+        const std::string hp = scene_dir + "/" + em->str;
+        std::string err;
+        int w, h;
+        std::vector<float> rgb;
+        if (load_hdr(hp, rgb, w, h, err)) s->sky = std::move(rgb), s->sky_w = w, s->sky_h = h;
+        else fprintf(stderr, "Error loading HDR emission of infinite_sphere '%s': %s. Using default background.\n", hp.c_str(), err.c_str());
+      } else if (em && parse_color(*em, c)) {
+        s->sky.assign(c, c + 3);
+        s->sky_w = s->sky_h = 1;
+      }
+    } else if (flags & PTH_LOAD_SKIP_UNKNOWN) {
+      fprintf(stderr, "Warning: primitive of unknown type `%s` skipped\n", t.c_str());
     } else {
       // serde: unknown variant of the internally tagged ObjectConfigVariant fails the whole file (parser.rs:135-165)
       throw std::runtime_error("unknown variant `" + t + "`, expected one of `sphere`, `plane`, `mesh`, `quad`, `cube`");
@@ -861,14 +939,15 @@ extern "C" {
 
 const char *pth_last_error(void) { return g_err.c_str(); }
 
-pth_scene *pth_load_scene_from_json(const char *json_path) {
+pth_scene *pth_load_scene_from_json_ex(const char *json_path, int flags) {
   try {
-    return load_scene(json_path);
+    return load_scene(json_path, flags);
   } catch (std::exception &e) {
     g_err = e.what();
     return nullptr;
   }
 }
+pth_scene *pth_load_scene_from_json(const char *json_path) { return pth_load_scene_from_json_ex(json_path, 0); }
 pth_scene *pth_scene_new(void) { return new pth_scene(); }
 void pth_scene_free(pth_scene *s) { delete s; }
 

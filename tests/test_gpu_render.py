@@ -15,7 +15,7 @@ import os
 import numpy as np
 import pytest
 
-from bindings import RNG_CHACHA, RNG_PHILOX, OracleScene, oracle_resolve
+from bindings import compare_hits, RNG_CHACHA, RNG_PHILOX, OracleScene, oracle_resolve
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -44,6 +44,20 @@ def _same_stream(pt, scene, w, h, spp, depth, seed=3):
                                                 ("veach-mis/scene.json", 160, 90, 16, 16)])        # C4 shrunk
 def test_same_stream_image_parity(pt, name, w, h, spp, depth):
     _same_stream(pt, pt.load_scene_from_json(os.path.join(SCENES, name)), w, h, spp, depth)
+
+
+def test_shipped_teapot_scene_with_loader_extensions(pt):
+    # the reference's own tungsten/teapot scene (infinite_sphere -> sky, WO3 meshes with 16-byte records: 124,840
+    # triangles, plastic + checker, HDR sky): closest hits and the same-stream image against the oracle
+    s = pt.load_scene_from_json(os.path.join(SCENES, "teapot", "scene.json"), pt.LOAD_INFINITE_SPHERE_SKY | pt.LOAD_WO3_STRIDE16)
+    cs = s.to_core().commit(0)
+    st = s.render_settings(width=320, height=180, spp=1, max_depth=1, seed=3)
+    o, d = cs.primary_rays(s.camera, st, 0)
+    got, _ = cs.intersect(o, d)
+    want = OracleScene(s).intersect(pt, o, d)
+    r = compare_hits(got, want)
+    assert r["id_mismatch"] == 0 and r["t_mismatch"] == 0 and r["bit_exact_records"] == r["both_hit"] > 20000, r
+    _same_stream(pt, s, 160, 90, 8, 12, seed=3)
 
 
 def test_config_c1_full_size_same_stream(pt):

@@ -218,3 +218,50 @@ def test_synthetic_scene_shape(pt):
     t = s.mesh(0)
     assert t.shape == (800, 12)
     assert t[:, [0, 3, 6]].min() == -50 and t[:, [0, 3, 6]].max() == 50
+
+
+def _wo3_reference_misread(path):
+    """Index triples exactly as Mesh::from_wo3 reads them (mesh_object.rs:188-190): 12 consecutive bytes per triangle
+    although the records are 16 bytes long; triples with an index out of range are dropped (:201-215)."""
+    raw = open(path, "rb").read()
+    nv = int(np.frombuffer(raw, "<u8", 1, 0)[0])
+    verts = np.frombuffer(raw, "<f4", nv * 8, 8).reshape(nv, 8)[:, :3]
+    off = 8 + nv * 32
+    nt = int(np.frombuffer(raw, "<u8", 1, off)[0])
+    words = np.frombuffer(raw, "<u4", nt * 4, off + 8)
+    wrong = words[:nt * 3].reshape(nt, 3)
+    right = words.reshape(nt, 4)[:, :3]
+    return verts, wrong[(wrong < nv).all(1)], right
+
+
+def test_shipped_teapot_scene_strict_and_extended(pt, scenes_dir):
+    path = os.path.join(scenes_dir, "teapot", "scene.json")
+    # the reference cannot load its own teapot scene: `infinite_sphere` is not an ObjectConfigVariant (parser.rs:136-165)
+    with pytest.raises(RuntimeError, match="unknown variant `infinite_sphere`"):
+        pt.load_scene_from_json(path)
+    s = pt.load_scene_from_json(path, pt.LOAD_INFINITE_SPHERE_SKY | pt.LOAD_WO3_STRIDE16)
+    assert s.settings == (1280, 720, 64, 64)
+    assert [o.type for o in s.objects] == [pt.OBJ_QUAD, pt.OBJ_MESH, pt.OBJ_MESH]
+    assert s.sky is not None and s.sky.shape == (512, 1024, 3)
+    mats = s.materials
+    assert mats[s.objects[1].material].type == pt.MAT_PLASTIC and mats[s.objects[0].material].type == pt.MAT_LAMBERT_CHECKER
+    # WO3: Tungsten's 16-byte records vs the reference's 12-byte mis-read, against an independent numpy reading
+    for obj, name in [(s.objects[1], "Mesh001.wo3"), (s.objects[2], "Mesh000.wo3")]:
+        verts, wrong, right = _wo3_reference_misread(os.path.join(scenes_dir, "teapot", "models", name))
+        tris = s.mesh(obj.mesh)
+        assert 0 < len(tris) <= len(right)
+        # every loaded triangle is one of the file's (degenerate ones are filtered)
+        v0 = {tuple(np.round(verts[t].ravel(), 6)) for t in right}
+        assert all(tuple(np.round(tr[:9], 6)) in v0 for tr in tris[:200])
+    strict_meshes = pt.load_scene_from_json(path, pt.LOAD_INFINITE_SPHERE_SKY)
+    for obj, name in [(strict_meshes.objects[1], "Mesh001.wo3"), (strict_meshes.objects[2], "Mesh000.wo3")]:
+        verts, wrong, right = _wo3_reference_misread(os.path.join(scenes_dir, "teapot", "models", name))
+        tris = strict_meshes.mesh(obj.mesh)
+        assert len(tris) <= len(wrong) < len(right)
+        w0 = {tuple(np.round(verts[t].ravel(), 6)) for t in wrong}
+        assert all(tuple(np.round(tr[:9], 6)) in w0 for tr in tris[:200])
+    # unknown types: fatal by default, skipped on request
+    with pytest.raises(RuntimeError, match="unknown variant"):
+        pt.load_scene_from_json(path, pt.LOAD_WO3_STRIDE16)
+    skipped = pt.load_scene_from_json(path, pt.LOAD_SKIP_UNKNOWN)
+    assert [o.type for o in skipped.objects] == [pt.OBJ_QUAD, pt.OBJ_MESH, pt.OBJ_MESH] and skipped.sky is None

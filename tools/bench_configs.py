@@ -48,6 +48,9 @@ def configs():
     c2 = pt.load_scene_from_json(os.path.join(SC, "semesterbild.json"))
     yield "C2 semesterbild 800x600x256spp depth 30", c2, 256, 8
     yield "C3 teapot (derived) 1280x720x512spp depth 64", teapot_scene(), 64, 2
+    c3s = pt.load_scene_from_json(os.path.join(SC, "teapot", "scene.json"), pt.LOAD_INFINITE_SPHERE_SKY | pt.LOAD_WO3_STRIDE16)
+    c3s.set_settings(1280, 720, 512, 64)
+    yield "C3s teapot as shipped (loader extensions: sky, WO3) 1280x720x512spp depth 64", c3s, 64, 2
     c4 = pt.load_scene_from_json(os.path.join(SC, "veach-mis", "scene.json"))
     yield "C4 veach-mis 1280x720x1024spp depth 16", c4, 128, 4
     c5 = pt.synthetic_scene(cells=1000)

@@ -14,6 +14,8 @@ Provenance (all relative to the reference root):
   data/scenes/tungsten/cornell-box/scene.json   -> scenes/cornell-box/scene.json   (config C1)
   data/scenes/tungsten/veach-mis/scene.json     -> scenes/veach-mis/scene.json     (config C4)
   data/models/teapot.obj                        -> scenes/teapot/teapot.obj        (config C3, derived scene)
+  data/scenes/tungsten/teapot/{scene.json, models/*.wo3, textures/envmap.hdr} -> scenes/teapot/   (the shipped teapot
+                                                   scene: fails to load in the reference; loads with the LOAD_* extensions)
 """
 import json
 import os
@@ -27,10 +29,14 @@ JSONS = [
     ("data/scenes/semesterbild.json", "semesterbild.json"),
     ("data/scenes/tungsten/cornell-box/scene.json", "cornell-box/scene.json"),
     ("data/scenes/tungsten/veach-mis/scene.json", "veach-mis/scene.json"),
+    ("data/scenes/tungsten/teapot/scene.json", "teapot/scene.json"),
 ]
 COPIES = [
     ("data/scenes/RayTracingText.obj", "RayTracingText.obj"),
     ("data/models/teapot.obj", "teapot/teapot.obj"),
+    ("data/scenes/tungsten/teapot/models/Mesh000.wo3", "teapot/models/Mesh000.wo3"),
+    ("data/scenes/tungsten/teapot/models/Mesh001.wo3", "teapot/models/Mesh001.wo3"),
+    ("data/scenes/tungsten/teapot/textures/envmap.hdr", "teapot/textures/envmap.hdr"),
 ]
 
 for src, dst in JSONS:
