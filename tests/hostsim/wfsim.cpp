@@ -99,7 +99,7 @@ struct Weights {
   double cull = 14, cull_setup = 12;
   double reject[5] = {30, 20, 40, 110, 190};   // sphere, plane, quad, cube, mesh (object ray + root test)
   double hit_extra[5] = {60, 15, 20, 170, 0};  // additional when a lane accepts the hit
-  double node = 230, tri = 70, turn = 28, refill = 70, finish = 12;
+  double node = 360, tri = 120, turn = 60, refill = 70, finish = 12;  // ncu, C2 (profiles/r1_v3_*): per executed step
   double barrier = 12;  // per warp per block barrier (issue + expected skew), a guess
 };
 
@@ -493,7 +493,46 @@ int sim_wavefront_model(sim_scene *ss, const ptc_camera *cam, const sim_model_pa
         pol.refill_lanes = mp->policy[p][0], pol.mode = mp->policy[p][1], pol.thr_node = mp->policy[p][2], pol.thr_tri = mp->policy[p][3];
         pol.tri_groups = mp->policy[p][4];
         std::vector<Task> copy = parked;
-        run_traverse(sc, copy, t_min, pol, w, tm[p]);
+        if (pol.mode >= 10) {  // tasks sorted by a spatial key before the traversal (v1 stepping policy)
+          const int variant = pol.mode;
+          pol.mode = 0;
+          std::vector<std::pair<uint32_t, uint32_t>> keys(copy.size());
+          for (size_t i = 0; i < copy.size(); i++) {
+            const Task &t = copy[i];
+            const DMesh &gm = sc.meshes[sc.objects[t.object].mesh];
+            const uint32_t oct = (t.d.x < 0 ? 1u : 0u) | (t.d.y < 0 ? 2u : 0u) | (t.d.z < 0 ? 4u : 0u);
+            uint32_t key = oct;
+            if (variant >= 11) {
+              // entry point of the ray into the root frame (variant 11) or its origin (12), 4 bits per axis, Morton order
+              float tn = 0.0f;
+              if (variant == 11) {
+                const float o[3] = {t.o.x, t.o.y, t.o.z}, d[3] = {t.d.x, t.d.y, t.d.z};
+                for (int a = 0; a < 3; a++) {
+                  const float inv = 1.0f / d[a];
+                  const float t0 = (gm.root_lo[a] - o[a]) * inv, t1 = (gm.root_hi[a] - o[a]) * inv;
+                  tn = fmaxf(tn, fminf(t0, t1));
+                }
+              }
+              const float pnt[3] = {t.o.x + t.d.x * tn, t.o.y + t.d.y * tn, t.o.z + t.d.z * tn};
+              uint32_t m = 0;
+              for (int a = 0; a < 3; a++) {
+                float u = (pnt[a] - gm.root_lo[a]) / std::max(gm.root_hi[a] - gm.root_lo[a], 1e-20f);
+                u = std::min(std::max(u, 0.0f), 0.999f);
+                const uint32_t q = (uint32_t)(u * 16.0f);
+                for (int b = 0; b < 4; b++) m |= ((q >> b) & 1u) << (3 * b + a);
+              }
+              key = (oct << 12) | m;
+            }
+            keys[i] = {key, (uint32_t)i};
+          }
+          std::stable_sort(keys.begin(), keys.end(), [](auto &a, auto &b) { return a.first < b.first; });
+          std::vector<Task> sorted(copy.size());
+          for (size_t i = 0; i < copy.size(); i++) sorted[i] = copy[keys[i].second];
+          run_traverse(sc, sorted, t_min, pol, w, tm[p]);
+          for (size_t i = 0; i < copy.size(); i++) copy[keys[i].second] = sorted[i];
+        } else {
+          run_traverse(sc, copy, t_min, pol, w, tm[p]);
+        }
         if (p == mp->n_policies - 1) parked.swap(copy);
       }
       // ---- post: finish + rest of the list
