@@ -18,7 +18,7 @@ CXXFLAGS := -O3 -std=c++17 -fPIC -ffp-contract=off -fno-fast-math -pthread -Wall
 all: $(PKG)/libptcore.so $(PKG)/libpthost.so oracle/liboracle.so tests/hostsim/libhostsim.so
 
 $(PKG)/libptcore.so: $(CSRC)/ptcore.cu $(CSRC)/pt_build.cpp $(HDRS)
-	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(CSRC)/ptcore.cu $(CSRC)/pt_build.cpp
+	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(CSRC)/ptcore.cu $(CSRC)/pt_build.cpp -ldl
 
 $(PKG)/libpthost.so: $(PKG)/host/pthost.cpp $(PKG)/host/json.hpp $(PKG)/libptcore.so include/pthost.h include/ptcore.h
 	$(CXX) $(CXXFLAGS) -shared -o $@ $(PKG)/host/pthost.cpp -L$(PKG) -lptcore -lz -Wl,-rpath,'$$ORIGIN'

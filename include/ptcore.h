@@ -169,6 +169,22 @@ int ptc_render_accumulate(ptc_scene *, const ptc_camera *, const ptc_render_sett
 int ptc_resolve_device(const float *d_rgb, int64_t n_pixels, float scale, uint32_t *d_out, void *cuda_stream);
 int ptc_resolve_u32(ptc_scene *, const float *rgb, int64_t n_pixels, float scale, uint32_t *out);
 
+/* In-process multi-GPU, for a single-process host like the reference's binary: the scene is replicated
+ * on every device of `devices` (devices[0] = the device `primary` was committed on; the host-side flattening is not
+ * repeated), one host thread per device renders its shard — a balanced sample range or the interleaved 32x32 tiles
+ * with index % n == i, Philox keyed on the global pixel / sample so the shards are invisible — and the fp32 radiance
+ * films are summed onto devices[0] with ONE ncclReduce over NVLink before the 1/spp scale and the copy to the host.
+ * The one-process-per-GPU route (ptc_render_accumulate + torch.distributed, bench.py) stays available.
+ * NCCL is loaded at run time (libnccl.so.2) by ptc_multi_create for n > 1 only. */
+typedef struct ptc_multi ptc_multi;
+enum { PTC_SHARD_SAMPLES = 0, PTC_SHARD_TILES = 1 };
+int ptc_multi_create(ptc_scene *primary, const int *devices, int n, ptc_multi **out);
+void ptc_multi_destroy(ptc_multi *);
+/* out_rgb as in ptc_render.  stats: paths / rays / launches summed over the devices, render_ms = host wall clock of the
+ * whole call.  settings->tile_mod must be 0. */
+int ptc_multi_render(ptc_multi *, const ptc_camera *, const ptc_render_settings *, int shard_mode, float *out_rgb,
+                     ptc_stats *stats);
+
 /* Parity hooks (host buffers in and out; each runs the SAME device functions the render kernels use). */
 /* HittableList::hit for n caller-provided rays (directions used as given). */
 int ptc_intersect(ptc_scene *, const float *origins, const float *dirs, int64_t n, float t_min, float t_max,

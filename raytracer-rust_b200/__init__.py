@@ -146,6 +146,10 @@ def core():
     L.ptc_primary_rays.argtypes = [_vp, C.POINTER(Camera), C.POINTER(RenderSettings), C.c_int32, _F, _F]
     L.ptc_scatter.argtypes = [_vp, C.c_int, _F, _F, _F, _vp, _F, C.c_int64, _vp, _F, _F, _F, _F]
     L.ptc_philox.argtypes = [_vp, _vp, _vp, _vp]
+    L.ptc_multi_create.argtypes = [_vp, C.POINTER(C.c_int), C.c_int, C.POINTER(_vp)]
+    L.ptc_multi_destroy.argtypes = [_vp]
+    L.ptc_multi_destroy.restype = None
+    L.ptc_multi_render.argtypes = [_vp, C.POINTER(Camera), C.POINTER(RenderSettings), C.c_int, _F, C.POINTER(Stats)]
     _core = L
     return L
 
@@ -439,6 +443,35 @@ def save_image(path, buffer_u32, width, height):
         raise RuntimeError(host().pth_last_error().decode())
 
 
+SHARD_SAMPLES, SHARD_TILES = 0, 1
+
+
+class MultiScene:
+    """A ptc_multi handle: one process, one host thread per GPU, one NCCL reduce of the film (include/ptcore.h)."""
+
+    def __init__(self, primary, devices):
+        self._primary = primary  # keeps the ptc_scene alive
+        devs = (C.c_int * len(devices))(*devices)
+        h = _vp()
+        _ck(core().ptc_multi_create(primary._h, devs, len(devices), C.byref(h)))
+        self._h = h
+        self.devices = list(devices)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                core().ptc_multi_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def render(self, camera, settings, shard=SHARD_SAMPLES):
+        out = np.empty((settings.height, settings.width, 3), np.float32)
+        st = Stats()
+        _ck(core().ptc_multi_render(self._h, C.byref(camera), C.byref(settings), shard, _fptr(out), C.byref(st)))
+        return out, st
+
+
 # ---------------------------------------------------------------------------------------------------------------
 class CoreScene:
     """A ptc_scene handle: the flattened scene on one B200."""
@@ -478,6 +511,10 @@ class CoreScene:
         st = Stats()
         _ck(core().ptc_render(self._h, C.byref(camera), C.byref(settings), _fptr(out), C.byref(st)))
         return out, st
+
+    def multi(self, devices):
+        """In-process multi-GPU (ptc_multi_*): this committed scene replicated on `devices` (devices[0] = its own)."""
+        return MultiScene(self, devices)
 
     def render_accumulate(self, camera, settings, d_accum_ptr, stream_ptr=None):
         st = Stats()

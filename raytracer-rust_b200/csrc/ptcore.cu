@@ -9,8 +9,13 @@
 //
 // There is no CPU fallback in this library: without a CUDA device commit / render / intersect return PTC_E_CUDA.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types and enums only: the library is bound at run time (see NcclApi)
 
 #include <algorithm>
+#include <chrono>
+#include <memory>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -392,6 +397,96 @@ int fail(int code, const std::string &msg) {
 
 }  // namespace
 
+// Device half of commit: upload the flattened scene `hs` (built) to `device` and fill s->ds.  `s` may be the handle that
+// owns `hs` (ptc_scene_commit) or a replica that only holds device state (ptc_multi_create).
+void upload_scene(ptc_scene *s, const HostScene &hs, int device) {
+  CK(cudaSetDevice(device));
+  s->device = device;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  s->sm_count = prop.multiProcessorCount;
+  std::vector<DMesh> dm;
+  for (auto &m : hs.meshes) {
+    auto nodes = std::make_unique<DevBuf<float4>>();
+    auto tris = std::make_unique<DevBuf<float4>>();
+    auto nrm = std::make_unique<DevBuf<float4>>();
+    nodes->upload(reinterpret_cast<const float4 *>(m->nodes.data()), m->nodes.size() * 5);
+    tris->upload(reinterpret_cast<const float4 *>(m->tri48.data()), m->tri48.size() * 3);
+    nrm->upload(m->normals.data(), m->normals.size());
+    const DMesh d = make_dmesh(*m, nodes->p, tris->p, nrm->p);
+    dm.push_back(d);
+    s->mesh_bufs.push_back(std::move(nodes));
+    s->mesh_bufs.push_back(std::move(tris));
+    s->mesh_bufs.push_back(std::move(nrm));
+  }
+  s->d_objects.upload(hs.objects.data(), hs.objects.size());
+  s->d_materials.upload(hs.materials.data(), hs.materials.size());
+  s->d_meshes.upload(dm.data(), dm.size());
+  if (!hs.sky.empty()) s->d_sky.upload(hs.sky.data(), hs.sky.size());
+  s->ds.objects = s->d_objects.p;
+  s->ds.materials = s->d_materials.p;
+  s->ds.meshes = s->d_meshes.p;
+  s->ds.sky = hs.sky.empty() ? nullptr : s->d_sky.p;
+  s->ds.n_objects = (int32_t)hs.objects.size();
+  s->ds.n_materials = (int32_t)hs.materials.size();
+  s->ds.n_meshes = (int32_t)dm.size();
+  s->ds.sky_w = hs.sky_w;
+  s->ds.sky_h = hs.sky_h;
+  s->mesh_objects = 0;
+  for (const DObject &o : hs.objects)
+    if (o.type == OBJ_MESH) s->mesh_objects++;
+  CK(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
+  s->committed = true;
+}
+
+// ---- in-process multi-GPU (ptc_multi_*): scene replicated per device, work sharded, ONE NCCL reduce of the film ----
+// NCCL is bound at run time: a process that also hosts PyTorch must end up with ONE libnccl (dlopen by soname returns
+// the copy that is already loaded), and processes that never call ptc_multi_create never load it.
+struct NcclApi {
+  void *lib = nullptr;
+  ncclResult_t (*GetVersion)(int *) = nullptr;
+  ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Reduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  void load() {
+    if (lib) return;
+    for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+      lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+      if (lib) break;
+    }
+    if (!lib) throw std::runtime_error(std::string("NCCL not found: ") + dlerror());
+    auto sym = [&](const char *n) {
+      void *p = dlsym(lib, n);
+      if (!p) throw std::runtime_error(std::string("NCCL symbol missing: ") + n);
+      return p;
+    };
+    GetVersion = reinterpret_cast<decltype(GetVersion)>(sym("ncclGetVersion"));
+    CommInitAll = reinterpret_cast<decltype(CommInitAll)>(sym("ncclCommInitAll"));
+    CommDestroy = reinterpret_cast<decltype(CommDestroy)>(sym("ncclCommDestroy"));
+    Reduce = reinterpret_cast<decltype(Reduce)>(sym("ncclReduce"));
+    GetErrorString = reinterpret_cast<decltype(GetErrorString)>(sym("ncclGetErrorString"));
+  }
+  void check(ncclResult_t r, const char *what) const {
+    if (r != ncclSuccess) throw CudaError(std::string(what) + ": " + (GetErrorString ? GetErrorString(r) : "NCCL error"));
+  }
+};
+
+struct ptc_multi {
+  ptc_scene *primary = nullptr;                     // devices[0]; not owned
+  std::vector<std::unique_ptr<ptc_scene>> replicas;  // devices[1..]: device state only
+  std::vector<ptc_scene *> scenes;
+  std::vector<int> devices;
+  std::vector<ncclComm_t> comms;  // empty for one device
+  NcclApi nccl;
+  ~ptc_multi() {
+    for (size_t i = 0; i < comms.size(); i++) {
+      cudaSetDevice(devices[i]);
+      if (comms[i]) nccl.CommDestroy(comms[i]);
+    }
+  }
+};
+
 // =============================================================================================================
 extern "C" {
 
@@ -487,43 +582,7 @@ int ptc_scene_commit(ptc_scene *s, int device) {
   }
   if (device < 0 || device >= n) throw std::invalid_argument("device index out of range");
   s->hs.build_all();  // host flattening: reference-BVH dead mask -> SAH -> 8-wide quantised BVH
-  CK(cudaSetDevice(device));
-  s->device = device;
-  cudaDeviceProp prop;
-  CK(cudaGetDeviceProperties(&prop, device));
-  s->sm_count = prop.multiProcessorCount;
-  std::vector<DMesh> dm;
-  for (auto &m : s->hs.meshes) {
-    auto nodes = std::make_unique<DevBuf<float4>>();
-    auto tris = std::make_unique<DevBuf<float4>>();
-    auto nrm = std::make_unique<DevBuf<float4>>();
-    nodes->upload(reinterpret_cast<const float4 *>(m->nodes.data()), m->nodes.size() * 5);
-    tris->upload(reinterpret_cast<const float4 *>(m->tri48.data()), m->tri48.size() * 3);
-    nrm->upload(m->normals.data(), m->normals.size());
-    const DMesh d = make_dmesh(*m, nodes->p, tris->p, nrm->p);
-    dm.push_back(d);
-    s->mesh_bufs.push_back(std::move(nodes));
-    s->mesh_bufs.push_back(std::move(tris));
-    s->mesh_bufs.push_back(std::move(nrm));
-  }
-  s->d_objects.upload(s->hs.objects.data(), s->hs.objects.size());
-  s->d_materials.upload(s->hs.materials.data(), s->hs.materials.size());
-  s->d_meshes.upload(dm.data(), dm.size());
-  if (!s->hs.sky.empty()) s->d_sky.upload(s->hs.sky.data(), s->hs.sky.size());
-  s->ds.objects = s->d_objects.p;
-  s->ds.materials = s->d_materials.p;
-  s->ds.meshes = s->d_meshes.p;
-  s->ds.sky = s->hs.sky.empty() ? nullptr : s->d_sky.p;
-  s->ds.n_objects = (int32_t)s->hs.objects.size();
-  s->ds.n_materials = (int32_t)s->hs.materials.size();
-  s->ds.n_meshes = (int32_t)dm.size();
-  s->ds.sky_w = s->hs.sky_w;
-  s->ds.sky_h = s->hs.sky_h;
-  s->mesh_objects = 0;
-  for (const DObject &o : s->hs.objects)
-    if (o.type == OBJ_MESH) s->mesh_objects++;
-  CK(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
-  s->committed = true;
+  upload_scene(s, s->hs, device);
   return 0;
   PTC_GUARD_END
 }
@@ -740,6 +799,112 @@ int ptc_philox(ptc_scene *s, const uint32_t ctr[4], const uint32_t key[2], uint3
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, d.p, 16, cudaMemcpyDeviceToHost, s->own_stream));
   CK(cudaStreamSynchronize(s->own_stream));
+  return 0;
+  PTC_GUARD_END
+}
+
+// ---- in-process multi-GPU ------------------------------------------------------------------------------------
+int ptc_multi_create(ptc_scene *primary, const int *devices, int n, ptc_multi **out) {
+  PTC_GUARD_BEGIN
+  require_committed(primary);
+  if (!devices || !out || n < 1) throw std::invalid_argument("bad argument");
+  if (devices[0] != primary->device) throw std::invalid_argument("devices[0] must be the device the scene was committed on");
+  int have = 0;
+  CK(cudaGetDeviceCount(&have));
+  for (int i = 0; i < n; i++) {
+    if (devices[i] < 0 || devices[i] >= have) throw std::invalid_argument("device index out of range");
+    for (int j = 0; j < i; j++)
+      if (devices[j] == devices[i]) throw std::invalid_argument("duplicate device");
+  }
+  std::unique_ptr<ptc_multi> m(new ptc_multi());
+  m->primary = primary;
+  m->devices.assign(devices, devices + n);
+  m->scenes.push_back(primary);
+  for (int i = 1; i < n; i++) {  // the host-side flattening (BVH build) is done once, by the primary
+    std::unique_ptr<ptc_scene> r(new ptc_scene());
+    upload_scene(r.get(), primary->hs, devices[i]);
+    m->scenes.push_back(r.get());
+    m->replicas.push_back(std::move(r));
+  }
+  if (n > 1) {
+    m->nccl.load();
+    m->comms.assign((size_t)n, nullptr);
+    m->nccl.check(m->nccl.CommInitAll(m->comms.data(), n, devices), "ncclCommInitAll");
+  }
+  CK(cudaSetDevice(primary->device));
+  *out = m.release();
+  return 0;
+  PTC_GUARD_END
+}
+
+void ptc_multi_destroy(ptc_multi *m) { delete m; }
+
+int ptc_multi_render(ptc_multi *m, const ptc_camera *cam, const ptc_render_settings *st, int shard_mode, float *out_rgb, ptc_stats *stats) {
+  PTC_GUARD_BEGIN
+  if (!m || !cam || !st || !out_rgb) throw std::invalid_argument("null argument");
+  if (st->width <= 0 || st->height <= 0 || st->spp <= 0) throw std::invalid_argument("bad render settings");
+  if (st->tile_mod > 0) throw std::invalid_argument("ptc_multi_render shards by itself: tile_mod must be 0");
+  if (shard_mode != PTC_SHARD_SAMPLES && shard_mode != PTC_SHARD_TILES) throw std::invalid_argument("bad shard mode");
+  const int n = (int)m->scenes.size();
+  int s_begin = st->sample_begin, s_end = st->sample_end;
+  if (s_begin == 0 && s_end == 0) s_end = st->spp;
+  if (s_begin < 0 || s_end < s_begin) throw std::invalid_argument("bad sample range");
+  const size_t count = (size_t)st->width * st->height * 3;
+  std::vector<ptc_stats> per((size_t)n);
+  std::vector<std::string> errors((size_t)n);
+  const auto t0 = std::chrono::steady_clock::now();
+  auto work = [&](int i) {
+    try {
+      ptc_scene *s = m->scenes[(size_t)i];
+      CK(cudaSetDevice(s->device));
+      if (s->w_film.n < count) s->w_film.alloc(count);
+      cudaStream_t stream = s->own_stream;
+      CK(cudaMemsetAsync(s->w_film.p, 0, count * sizeof(float), stream));
+      ptc_render_settings mine = *st;
+      bool idle = false;
+      if (shard_mode == PTC_SHARD_SAMPLES) {  // contiguous, balanced split of the sample range
+        const int total = s_end - s_begin, base = total / n, rem = total % n;
+        mine.sample_begin = s_begin + i * base + std::min(i, rem);
+        mine.sample_end = mine.sample_begin + base + (i < rem ? 1 : 0);
+        idle = mine.sample_end == mine.sample_begin;
+      } else {  // interleaved 32x32 tiles
+        mine.sample_begin = s_begin, mine.sample_end = s_end;
+        mine.tile_mod = n, mine.tile_rem = i;
+      }
+      memset(&per[(size_t)i], 0, sizeof(ptc_stats));
+      if (!idle) render_accumulate(s, cam, &mine, s->w_film.p, stream, &per[(size_t)i]);
+      // the single exchange step of the path: sum of the radiance films to devices[0]
+      if (n > 1) m->nccl.check(m->nccl.Reduce(s->w_film.p, s->w_film.p, count, ncclFloat, ncclSum, 0, m->comms[(size_t)i], stream), "ncclReduce");
+      CK(cudaStreamSynchronize(stream));
+    } catch (std::exception &e) {
+      errors[(size_t)i] = e.what();
+    }
+  };
+  std::vector<std::thread> threads;
+  for (int i = 1; i < n; i++) threads.emplace_back(work, i);
+  work(0);
+  for (auto &t : threads) t.join();
+  for (int i = 0; i < n; i++)
+    if (!errors[(size_t)i].empty()) throw CudaError("device " + std::to_string(m->devices[(size_t)i]) + ": " + errors[(size_t)i]);
+  ptc_scene *root = m->primary;
+  CK(cudaSetDevice(root->device));
+  if (root->w_film_out.n < count) root->w_film_out.alloc(count);
+  const float inv_spp = 1.0f / (float)st->spp;  // renderer.rs:85
+  k_scale<<<(unsigned)((count + 255) / 256), 256, 0, root->own_stream>>>(root->w_film.p, root->w_film_out.p, count, inv_spp);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out_rgb, root->w_film_out.p, count * sizeof(float), cudaMemcpyDeviceToHost, root->own_stream));
+  CK(cudaStreamSynchronize(root->own_stream));
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    for (const ptc_stats &p : per) {
+      stats->paths += p.paths, stats->rays += p.rays, stats->kernel_launches += p.kernel_launches;
+      stats->iterations = std::max(stats->iterations, p.iterations);
+      stats->nodes_visited += p.nodes_visited, stats->tris_tested += p.tris_tested, stats->mesh_rays += p.mesh_rays;
+    }
+    stats->kernel_launches += 1;
+    // wall clock of the whole call on the host: renders on all devices, the reduce, the scale and the copy out
+    stats->render_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  }
   return 0;
   PTC_GUARD_END
 }

@@ -109,4 +109,17 @@ extern "C" {
                                  cuda_stream: *mut c_void, stats: *mut ptc_stats) -> c_int;
     pub fn ptc_resolve_u32(s: *mut ptc_scene, rgb: *const f32, n_pixels: i64, scale: f32, out: *mut u32) -> c_int;
     pub fn ptc_resolve_device(d_rgb: *const f32, n_pixels: i64, scale: f32, d_out: *mut u32, cuda_stream: *mut c_void) -> c_int;
+
+    // in-process multi-GPU: one host thread per device inside the library, one ncclReduce of the film (include/ptcore.h)
+    pub fn ptc_multi_create(primary: *mut ptc_scene, devices: *const c_int, n: c_int, out: *mut *mut ptc_multi) -> c_int;
+    pub fn ptc_multi_destroy(m: *mut ptc_multi);
+    pub fn ptc_multi_render(m: *mut ptc_multi, cam: *const ptc_camera, st: *const ptc_render_settings, shard_mode: c_int,
+                            out_rgb: *mut f32, stats: *mut ptc_stats) -> c_int;
 }
+
+#[repr(C)]
+pub struct ptc_multi {
+    _private: [u8; 0],
+}
+pub const PTC_SHARD_SAMPLES: c_int = 0;
+pub const PTC_SHARD_TILES: c_int = 1;

@@ -1,0 +1,46 @@
+"""ptc_multi_*: the in-process multi-GPU path of the C ABI (one host thread per GPU, one NCCL reduce of the film).
+Needs two GPUs; on a one-GPU box only the single-device degenerate case runs."""
+import os
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SCENES = os.path.join(ROOT, "scenes")
+pytestmark = pytest.mark.gpu
+
+
+def _scene(pt):
+    s = pt.load_scene_from_json(os.path.join(SCENES, "semesterbild.json"))
+    return s, s.to_core().commit(0)
+
+
+def test_multi_single_device_equals_render(pt):
+    s, cs = _scene(pt)
+    st = s.render_settings(width=120, height=90, spp=6, max_depth=8, seed=2)
+    whole, ws = cs.render(s.camera, st)
+    for shard in (pt.SHARD_SAMPLES, pt.SHARD_TILES):
+        img, ms = cs.multi([0]).render(s.camera, st, shard)
+        assert np.allclose(img, whole, rtol=1e-5, atol=1e-6) and ms.rays == ws.rays and ms.paths == ws.paths
+    with pytest.raises(pt.PtcError):
+        cs.multi([0, 0])  # duplicate device
+    with pytest.raises(pt.PtcError):
+        cs.multi([1] if pt.device_count() > 1 else [7])  # devices[0] must be the scene's device / out of range
+
+
+@pytest.mark.skipif("__import__('ptload').load().device_count() < 2")
+def test_multi_two_devices_shards_are_invisible(pt):
+    s, cs = _scene(pt)
+    n = min(pt.device_count(), 4)
+    m = cs.multi(list(range(n)))
+    st = s.render_settings(width=200, height=150, spp=8, max_depth=30, seed=5)
+    whole, ws = cs.render(s.camera, st)
+    for shard in (pt.SHARD_SAMPLES, pt.SHARD_TILES):
+        img, ms = m.render(s.camera, st, shard)
+        assert ms.paths == ws.paths == 200 * 150 * 8 and ms.rays == ws.rays
+        assert np.allclose(img, whole, rtol=1e-5, atol=1e-6)
+    # more devices than samples: sample sharding leaves devices idle, the image is still the whole image
+    st1 = s.render_settings(width=64, height=48, spp=1, max_depth=4, seed=5)
+    a, _ = cs.render(s.camera, st1)
+    b, _ = m.render(s.camera, st1, pt.SHARD_SAMPLES)
+    assert np.allclose(a, b, rtol=1e-5, atol=1e-6)
