@@ -10,8 +10,8 @@ reference times it: renderer.rs:82,109 — scene load, BVH build and PNG encode 
 
   value  device-resident: scene resident in HBM, film accumulated in HBM (ptc_render_accumulate) and, for N > 1, one
          NCCL reduce of the fp32 film to rank 0 + the film resolve, all inside the timed region.
-  e2e    the reference-facing call with HOST buffers: ptc_render (film copied to the host) + ptc_resolve_u32
-         (host in, host out), i.e. `render_scene` returning its Vec<u32>.
+  e2e    the reference-facing call with HOST buffers: ptc_render_u32, i.e. `render_scene` returning its Vec<u32>
+         (film resolved on the device, packed image copied to the host).
 N > 1 is weak scaling over samples: every rank renders the full frame at the config's spp with its own sample
 range [rank*spp, (rank+1)*spp) of an N*spp job (Philox is keyed on the global sample index, so the reduced film is
 the N*spp image); value = all ranks' paths / max-over-ranks time.
@@ -215,8 +215,7 @@ def main():
     def step_e2e():
         # the reference-facing call: host buffers in and out
         if world == 1:
-            img, st = cs.render(cam, settings())
-            cs.resolve_u32(img)
+            _, st = cs.render_u32(cam, settings())  # render_scene -> Vec<u32>, resolved on the device
             return st
         st = step_device()
         if rank == 0:
@@ -276,8 +275,8 @@ def main():
         dist.all_reduce(e2e_paths, op=dist.ReduceOp.SUM)
     e2e_value = float(e2e_paths.item()) / ms_e2e / 1e3
     if world == 1:
-        d2h = h * w * 3 * 4 + h * w * 4  # film to the host, packed image to the host
-        h2d = h * w * 3 * 4 + 256          # film back in for ptc_resolve_u32 + control block / launch parameters
+        d2h = h * w * 4 + 64 * (1 + spp // 8)  # the packed image + the control-block snapshots the host polls
+        h2d = 256                               # control block + launch parameters (the scene is resident)
     else:
         d2h, h2d = h * w * 4, 256
 

@@ -160,6 +160,9 @@ int ptc_scene_mesh_info(const ptc_scene *, int object, ptc_mesh_info *info, uint
 /* render_scene up to `image_data` (renderer.rs:83-106): out_rgb = W*H*3 floats on the HOST, linear mean
  * radiance (sum over this call's samples / spp).  Includes the device->host copy. */
 int ptc_render(ptc_scene *, const ptc_camera *, const ptc_render_settings *, float *out_rgb, ptc_stats *stats);
+/* render_scene as a whole (renderer.rs:67-123): out_u32 = W*H pixels 0x00RRGGBB on the HOST, row-major, top row first —
+ * the Vec<u32> the reference returns.  The film is resolved on the device; only W*H*4 bytes cross PCIe. */
+int ptc_render_u32(ptc_scene *, const ptc_camera *, const ptc_render_settings *, uint32_t *out_u32, ptc_stats *stats);
 /* Same, device-resident: ADDS this call's radiance sum (not divided by spp) into d_accum (W*H*3 floats in
  * device memory of the scene's device), ordered on `cuda_stream` (a cudaStream_t, NULL = default stream).
  * Returns after the work is enqueued AND finished (the wavefront loop polls its queue counters). */

@@ -139,6 +139,7 @@ def core():
     L.ptc_scene_commit.argtypes = [_vp, C.c_int]
     L.ptc_scene_mesh_info.argtypes = [_vp, C.c_int, C.POINTER(MeshInfo), _vp, _vp]
     L.ptc_render.argtypes = [_vp, C.POINTER(Camera), C.POINTER(RenderSettings), _F, C.POINTER(Stats)]
+    L.ptc_render_u32.argtypes = [_vp, C.POINTER(Camera), C.POINTER(RenderSettings), _vp, C.POINTER(Stats)]
     L.ptc_render_accumulate.argtypes = [_vp, C.POINTER(Camera), C.POINTER(RenderSettings), _vp, _vp, C.POINTER(Stats)]
     L.ptc_resolve_device.argtypes = [_vp, C.c_int64, C.c_float, _vp, _vp]
     L.ptc_resolve_u32.argtypes = [_vp, _F, C.c_int64, C.c_float, _vp]
@@ -510,6 +511,13 @@ class CoreScene:
         out = np.empty((settings.height, settings.width, 3), np.float32)
         st = Stats()
         _ck(core().ptc_render(self._h, C.byref(camera), C.byref(settings), _fptr(out), C.byref(st)))
+        return out, st
+
+    def render_u32(self, camera, settings):
+        """-> (H*W uint32 0x00RRGGBB = the Vec<u32> of renderer.rs:67-123, Stats); resolved on the device."""
+        out = np.empty(settings.height * settings.width, np.uint32)
+        st = Stats()
+        _ck(core().ptc_render_u32(self._h, C.byref(camera), C.byref(settings), out.ctypes.data, C.byref(st)))
         return out, st
 
     def multi(self, devices):

@@ -674,6 +674,28 @@ int ptc_render(ptc_scene *s, const ptc_camera *cam, const ptc_render_settings *s
   PTC_GUARD_END
 }
 
+int ptc_render_u32(ptc_scene *s, const ptc_camera *cam, const ptc_render_settings *st, uint32_t *out_u32, ptc_stats *stats) {
+  PTC_GUARD_BEGIN
+  require_committed(s);
+  if (!st || !out_u32) throw std::invalid_argument("null argument");
+  if (st->width <= 0 || st->height <= 0 || st->spp <= 0) throw std::invalid_argument("bad render settings");
+  CK(cudaSetDevice(s->device));
+  const size_t px = (size_t)st->width * st->height, n = px * 3;
+  if (s->w_film.n < n) s->w_film.alloc(n);
+  if (s->w_packed.n < px) s->w_packed.alloc(px);
+  cudaStream_t stream = s->own_stream;
+  CK(cudaMemsetAsync(s->w_film.p, 0, n * sizeof(float), stream));
+  render_accumulate(s, cam, st, s->w_film.p, stream, stats);
+  // renderer.rs:103 (x 1/spp) and :112-120 (sqrt, clamp, x255, truncate, pack) on the device: only the packed image crosses PCIe
+  k_resolve<<<(unsigned)((px + 255) / 256), 256, 0, stream>>>(s->w_film.p, px, 1.0f / (float)st->spp, s->w_packed.p);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out_u32, s->w_packed.p, px * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+  CK(cudaStreamSynchronize(stream));
+  if (stats) stats->kernel_launches += 1;
+  return 0;
+  PTC_GUARD_END
+}
+
 int ptc_resolve_device(const float *d_rgb, int64_t n_pixels, float scale, uint32_t *d_out, void *cuda_stream) {
   PTC_GUARD_BEGIN
   if (!d_rgb || !d_out || n_pixels < 0) throw std::invalid_argument("bad argument");

@@ -1177,9 +1177,7 @@ int pth_render_scene(const pth_scene *s, int device, uint32_t *out_u32, ptc_stat
     ptc_render_settings st;
     memset(&st, 0, sizeof(st));
     st.width = s->width, st.height = s->height, st.spp = s->spp, st.max_depth = s->max_depth;
-    std::vector<float> rgb((size_t)s->width * s->height * 3);
-    r = ptc_render(c, &s->camera, &st, rgb.data(), stats);
-    if (r == 0) r = ptc_resolve_u32(c, rgb.data(), (int64_t)s->width * s->height, 1.0f, out_u32);
+    r = ptc_render_u32(c, &s->camera, &st, out_u32, stats);
   }
   if (r != 0) g_err = ptc_last_error();
   ptc_scene_destroy(c);

@@ -211,6 +211,19 @@ def test_render_scene_entry_point_and_png(pt, tmp_path):
     assert os.path.getsize(tmp_path / "c.png") > 100
 
 
+def test_render_u32_is_render_then_resolve(pt):
+    s = pt.load_scene_from_json(os.path.join(SCENES, "cornell-box", "scene.json"))
+    cs = s.to_core().commit(0)
+    st = s.render_settings(width=96, height=64, spp=4, max_depth=6, seed=9)
+    img, a = cs.render(s.camera, st)
+    packed, b = cs.render_u32(s.camera, st)
+    assert a.rays == b.rays and packed.shape == (96 * 64,)
+    want = cs.resolve_u32(img)
+    # the film sums are float atomics (order varies run to run): a channel may land on the other side of a truncation
+    diff = np.abs(((packed[:, None] >> np.array([16, 8, 0])) & 255).astype(int) - ((want[:, None] >> np.array([16, 8, 0])) & 255).astype(int))
+    assert diff.max() <= 1 and (diff > 0).mean() < 0.01
+
+
 def test_commit_twice_and_bad_device(pt):
     s = pt.Scene()
     m = s.add_material(pt.lambertian((1, 1, 1)))
