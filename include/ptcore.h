@@ -187,6 +187,9 @@ void ptc_multi_destroy(ptc_multi *);
  * whole call.  settings->tile_mod must be 0. */
 int ptc_multi_render(ptc_multi *, const ptc_camera *, const ptc_render_settings *, int shard_mode, float *out_rgb,
                      ptc_stats *stats);
+/* out_u32 as in ptc_render_u32 (resolved on devices[0]) */
+int ptc_multi_render_u32(ptc_multi *, const ptc_camera *, const ptc_render_settings *, int shard_mode, uint32_t *out_u32,
+                         ptc_stats *stats);
 
 /* Parity hooks (host buffers in and out; each runs the SAME device functions the render kernels use). */
 /* HittableList::hit for n caller-provided rays (directions used as given). */

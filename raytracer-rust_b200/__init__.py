@@ -151,6 +151,7 @@ def core():
     L.ptc_multi_destroy.argtypes = [_vp]
     L.ptc_multi_destroy.restype = None
     L.ptc_multi_render.argtypes = [_vp, C.POINTER(Camera), C.POINTER(RenderSettings), C.c_int, _F, C.POINTER(Stats)]
+    L.ptc_multi_render_u32.argtypes = [_vp, C.POINTER(Camera), C.POINTER(RenderSettings), C.c_int, _vp, C.POINTER(Stats)]
     _core = L
     return L
 
@@ -470,6 +471,12 @@ class MultiScene:
         out = np.empty((settings.height, settings.width, 3), np.float32)
         st = Stats()
         _ck(core().ptc_multi_render(self._h, C.byref(camera), C.byref(settings), shard, _fptr(out), C.byref(st)))
+        return out, st
+
+    def render_u32(self, camera, settings, shard=SHARD_SAMPLES):
+        out = np.empty(settings.height * settings.width, np.uint32)
+        st = Stats()
+        _ck(core().ptc_multi_render_u32(self._h, C.byref(camera), C.byref(settings), shard, out.ctypes.data, C.byref(st)))
         return out, st
 
 

@@ -892,9 +892,10 @@ int ptc_multi_create(ptc_scene *primary, const int *devices, int n, ptc_multi **
 
 void ptc_multi_destroy(ptc_multi *m) { delete m; }
 
-int ptc_multi_render(ptc_multi *m, const ptc_camera *cam, const ptc_render_settings *st, int shard_mode, float *out_rgb, ptc_stats *stats) {
+static int multi_render(ptc_multi *m, const ptc_camera *cam, const ptc_render_settings *st, int shard_mode, float *out_rgb, uint32_t *out_u32,
+                        ptc_stats *stats) {
   PTC_GUARD_BEGIN
-  if (!m || !cam || !st || !out_rgb) throw std::invalid_argument("null argument");
+  if (!m || !cam || !st || (!out_rgb && !out_u32)) throw std::invalid_argument("null argument");
   if (st->width <= 0 || st->height <= 0 || st->spp <= 0) throw std::invalid_argument("bad render settings");
   if (st->tile_mod > 0) throw std::invalid_argument("ptc_multi_render shards by itself: tile_mod must be 0");
   if (shard_mode != PTC_SHARD_SAMPLES && shard_mode != PTC_SHARD_TILES) throw std::invalid_argument("bad shard mode");
@@ -941,11 +942,19 @@ int ptc_multi_render(ptc_multi *m, const ptc_camera *cam, const ptc_render_setti
     if (!errors[(size_t)i].empty()) throw CudaError("device " + std::to_string(m->devices[(size_t)i]) + ": " + errors[(size_t)i]);
   ptc_scene *root = m->primary;
   CK(cudaSetDevice(root->device));
-  if (root->w_film_out.n < count) root->w_film_out.alloc(count);
   const float inv_spp = 1.0f / (float)st->spp;  // renderer.rs:85
-  k_scale<<<(unsigned)((count + 255) / 256), 256, 0, root->own_stream>>>(root->w_film.p, root->w_film_out.p, count, inv_spp);
-  CK(cudaGetLastError());
-  film_to_host(root, root->w_film_out.p, out_rgb, count, root->own_stream);
+  if (out_rgb) {
+    if (root->w_film_out.n < count) root->w_film_out.alloc(count);
+    k_scale<<<(unsigned)((count + 255) / 256), 256, 0, root->own_stream>>>(root->w_film.p, root->w_film_out.p, count, inv_spp);
+    CK(cudaGetLastError());
+    film_to_host(root, root->w_film_out.p, out_rgb, count, root->own_stream);
+  } else {  // renderer.rs:103,112-120 on the device; the packed image is a third of the film
+    const size_t px = count / 3;
+    if (root->w_packed.n < px) root->w_packed.alloc(px);
+    k_resolve<<<(unsigned)((px + 255) / 256), 256, 0, root->own_stream>>>(root->w_film.p, px, inv_spp, root->w_packed.p);
+    CK(cudaGetLastError());
+    film_to_host(root, reinterpret_cast<const float *>(root->w_packed.p), reinterpret_cast<float *>(out_u32), px, root->own_stream);
+  }
   if (stats) {
     memset(stats, 0, sizeof(*stats));
     for (const ptc_stats &p : per) {
@@ -959,6 +968,16 @@ int ptc_multi_render(ptc_multi *m, const ptc_camera *cam, const ptc_render_setti
   }
   return 0;
   PTC_GUARD_END
+}
+
+int ptc_multi_render(ptc_multi *m, const ptc_camera *cam, const ptc_render_settings *st, int shard_mode, float *out_rgb, ptc_stats *stats) {
+  if (!out_rgb) return fail(PTC_E_INVALID, "null argument");
+  return multi_render(m, cam, st, shard_mode, out_rgb, nullptr, stats);
+}
+int ptc_multi_render_u32(ptc_multi *m, const ptc_camera *cam, const ptc_render_settings *st, int shard_mode, uint32_t *out_u32,
+                         ptc_stats *stats) {
+  if (!out_u32) return fail(PTC_E_INVALID, "null argument");
+  return multi_render(m, cam, st, shard_mode, nullptr, out_u32, stats);
 }
 
 }  // extern "C"

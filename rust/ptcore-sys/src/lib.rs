@@ -115,6 +115,8 @@ extern "C" {
     // in-process multi-GPU: one host thread per device inside the library, one ncclReduce of the film (include/ptcore.h)
     pub fn ptc_multi_create(primary: *mut ptc_scene, devices: *const c_int, n: c_int, out: *mut *mut ptc_multi) -> c_int;
     pub fn ptc_multi_destroy(m: *mut ptc_multi);
+    pub fn ptc_multi_render_u32(m: *mut ptc_multi, cam: *const ptc_camera, st: *const ptc_render_settings, shard_mode: c_int,
+                                out_u32: *mut u32, stats: *mut ptc_stats) -> c_int;
     pub fn ptc_multi_render(m: *mut ptc_multi, cam: *const ptc_camera, st: *const ptc_render_settings, shard_mode: c_int,
                             out_rgb: *mut f32, stats: *mut ptc_stats) -> c_int;
 }

@@ -22,6 +22,10 @@ def test_multi_single_device_equals_render(pt):
     for shard in (pt.SHARD_SAMPLES, pt.SHARD_TILES):
         img, ms = cs.multi([0]).render(s.camera, st, shard)
         assert np.allclose(img, whole, rtol=1e-5, atol=1e-6) and ms.rays == ws.rays and ms.paths == ws.paths
+    packed, _ = cs.multi([0]).render_u32(s.camera, st)
+    want, _ = cs.render_u32(s.camera, st)
+    ch = lambda a: ((a[:, None] >> np.array([16, 8, 0])) & 255).astype(int)  # noqa: E731
+    assert np.abs(ch(packed) - ch(want)).max() <= 1
     with pytest.raises(pt.PtcError):
         cs.multi([0, 0])  # duplicate device
     with pytest.raises(pt.PtcError):

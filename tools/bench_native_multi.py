@@ -5,7 +5,8 @@ torch, no torchrun) on 1..N GPUs of this node: the route a single-process host s
   python tools/bench_native_multi.py --config c5 --spp 64 --gpus 1,2,4,8 [--shard tiles|samples] [--steps 3]
 
 The job is FIXED (the config's frame at --spp samples): strong scaling.  Times are host wall clock around the whole
-call (renders on all devices + reduce + 1/spp scale + copy of the film to the host), i.e. end to end with HOST buffers.
+call (renders on all devices + reduce + film resolve on device 0 + copy of the packed image to the host), i.e. end to
+end with HOST buffers, like `render_scene` returning its Vec<u32>.
 """
 import argparse
 import json
@@ -40,18 +41,19 @@ def main():
         if n > have:
             continue
         m = cs.multi(list(range(n)))
-        m.render(scene.camera, st, shard)  # warm-up: pools, NCCL channels
+        m.render_u32(scene.camera, st, shard)  # warm-up: pools, NCCL channels
         best, tot, stats = None, 0.0, None
         for _ in range(a.steps):
             t0 = time.perf_counter()
-            _, stats = m.render(scene.camera, st, shard)
+            _, stats = m.render_u32(scene.camera, st, shard)  # render_scene's Vec<u32>: the film is resolved on device 0
             dt = (time.perf_counter() - t0) * 1e3
             tot += dt
             best = dt if best is None else min(best, dt)
         ms = tot / a.steps
         print(json.dumps({"config": label, "path": "ptc_multi_render (in-process, NCCL reduce)", "n_gpus": n, "sharding": a.shard,
                           "spp": a.spp, "steps": a.steps, "ms_per_step": ms, "best_ms": best, "mpaths_per_s": stats.paths / ms / 1e3,
-                          "mrays_per_s": stats.rays / ms / 1e3, "film_bytes": st.width * st.height * 12}), flush=True)
+                          "mrays_per_s": stats.rays / ms / 1e3, "film_reduce_bytes": st.width * st.height * 12 if n > 1 else 0,
+                          "d2h_bytes": st.width * st.height * 4}), flush=True)
         del m
 
 
