@@ -39,11 +39,12 @@ METRIC = "Mpaths/s (semesterbild 800x600x256spp, depth 30)"
 
 def measured_traffic():
     """DRAM bytes per extend ray from the committed ncu capture (dram__bytes_read.sum + dram__bytes_write.sum of the three
-    extend kernels of one full-pool iteration, profiles/r1_extend_traffic.json)."""
+    extend kernels of one full-pool iteration, profiles/r1_extend_traffic.json), and that capture's per-kernel figures."""
     p = os.path.join(ROOT, "profiles", "r1_extend_traffic.json")
     if os.path.exists(p):
-        return float(json.load(open(p))["dram_bytes_per_ray"])
-    return None
+        d = json.load(open(p))
+        return float(d["dram_bytes_per_ray"]), d.get("ncu_per_kernel")
+    return None, None
 
 
 def peaks():
@@ -301,7 +302,7 @@ def main():
     fp32_peak = sms * 128 * sm_mhz * 1e6 / 1e12  # T instr/s at the clock sampled under load
     achieved_tinstr = instr_per_ray * rays_rank / ext_s / 1e12 if ext_s > 0 else 0.0
 
-    dram_per_ray = measured_traffic()
+    dram_per_ray, ncu_kernels = measured_traffic()
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -335,7 +336,11 @@ def main():
                                  "the stage is instruction-issue bound (profiles/), see roofline_fp32"},
             "roofline_fp32": {"bound": "fp32 issue", "achieved": achieved_tinstr, "peak": fp32_peak, "unit": "Tinstr/s",
                               "frac": achieved_tinstr / fp32_peak, "algorithmic_instr_per_ray": instr_per_ray,
-                              "peak_source": f"{sms} SMs x 128 lanes x {sm_mhz:.0f} MHz sampled under load"},
+                              "peak_source": f"{sms} SMs x 128 lanes x {sm_mhz:.0f} MHz sampled under load",
+                              "ncu": ncu_kernels,
+                              "note": "algorithmic count with FMA = 1 and no divergence; what the kernels EXECUTE (unfused IEEE "
+                                      "arithmetic for bit-exact hit records, incoherent rays) keeps the issue slots busy 76 % / 66 % / "
+                                      "42 % of the time in pre / traverse / post (ncu, profiles/r1_v3_stages_ncu_summary.txt)"},
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(pt, scene)
