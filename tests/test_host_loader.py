@@ -265,3 +265,31 @@ def test_shipped_teapot_scene_strict_and_extended(pt, scenes_dir):
         pt.load_scene_from_json(path, pt.LOAD_WO3_STRIDE16)
     skipped = pt.load_scene_from_json(path, pt.LOAD_SKIP_UNKNOWN)
     assert [o.type for o in skipped.objects] == [pt.OBJ_QUAD, pt.OBJ_MESH, pt.OBJ_MESH] and skipped.sky is None
+
+
+def test_reference_bvh_restatement_radix_equals_stable_sort(scenes_dir):
+    """pt_build sorts big nodes with an LSD radix sort on the centroid's order-preserving integer image; it must produce
+    the permutation std::stable_sort produces (dead mask, DFS leaf order, node / leaf / depth counts), here on the two
+    WO3 meshes of the shipped teapot scene (76,968 and 47,872 triangles).  The switch is read once per process."""
+    import subprocess
+    import sys
+    prog = (
+        "import sys, hashlib; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import ptload; pt = ptload.load()\n"
+        "from bindings import SimScene\n"
+        "s = pt.load_scene_from_json(%r, pt.LOAD_INFINITE_SPHERE_SKY | pt.LOAD_WO3_STRIDE16)\n"
+        "sim = SimScene(s)\n"
+        "for k, o in enumerate(s.objects):\n"
+        "    if o.type == pt.OBJ_MESH:\n"
+        "        info, dead, order = sim.mesh_info(pt, k)\n"
+        "        print(info.ref_nodes, info.ref_leaves, info.ref_depth, info.live_triangles, hashlib.md5(dead.tobytes()).hexdigest(),\n"
+        "              hashlib.md5(order.tobytes()).hexdigest())\n"
+    ) % (os.path.dirname(scenes_dir), os.path.join(os.path.dirname(scenes_dir), "tests"), os.path.join(scenes_dir, "teapot", "scene.json"))
+    outs = []
+    for force in ("", "1"):
+        env = dict(os.environ)
+        env.pop("PTC_REF_STABLE_SORT", None)
+        if force:
+            env["PTC_REF_STABLE_SORT"] = force
+        outs.append(subprocess.run([sys.executable, "-c", prog], env=env, capture_output=True, text=True, check=True).stdout)
+    assert outs[0] == outs[1] and len(outs[0].splitlines()) == 2
