@@ -51,6 +51,19 @@ PT_HD float byte_as_unit_float(uint32_t packed) {
 #endif
 }
 
+// (r0, r1) = (a0, a1) * b + c with b, c scalars: ONE packed FFMA2 on the device (conservative box arithmetic only; the
+// host build computes the same two fused products)
+PT_HD void fma2_bcast(float &r0, float &r1, float a0, float a1, float b, float c) {
+#if defined(__CUDA_ARCH__)
+  asm("{ .reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%4}; mov.b64 rc, {%5,%5}; fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0,%1}, rd; }"
+      : "=f"(r0), "=f"(r1)
+      : "f"(a0), "f"(a1), "f"(b), "f"(c));
+#else
+  r0 = fmaf(a0, b, c);
+  r1 = fmaf(a1, b, c);
+#endif
+}
+
 struct TravState {
   V3 o, d;             // object-space ray
   float idx, idy, idz;  // 1/d for the slab tests
@@ -120,20 +133,25 @@ PT_HD void trav_node(const DMesh &m, TravState &s, uint2 *stack, int &sp, Traver
     const uint32_t inner_mask4 = (is_inner4 >> 4) * 0xffu;
     const uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1f1f1f1fu;
     const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
-#define PT_CHILD(J)                                                                                       \
-  {                                                                                                       \
-    const float tnx = fmaf(byte_as_unit_float<J>(nx[h]), adjx, orgx);                                     \
-    const float tny = fmaf(byte_as_unit_float<J>(ny[h]), adjy, orgy);                                     \
-    const float tnz = fmaf(byte_as_unit_float<J>(nz[h]), adjz, orgz);                                     \
-    const float tfx = fmaf(byte_as_unit_float<J>(fx[h]), adjx, orgx);                                     \
-    const float tfy = fmaf(byte_as_unit_float<J>(fy[h]), adjy, orgy);                                     \
-    const float tfz = fmaf(byte_as_unit_float<J>(fz[h]), adjz, orgz);                                     \
-    /* fmaxf / fminf drop NaN operands (0 * inf from axis-parallel rays): the slab then does not constrain */ \
-    const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, s.t_min));                                          \
-    const float tf = fminf(fminf(tfx, tfy), fminf(tfz, s.best_t));                                         \
-    if (tn <= tf) hitmask |= ((child_bits4 >> (8 * J)) & 0xffu) << ((bit_index4 >> (8 * J)) & 0xffu);      \
+    // Two children per instruction: sm_100a's packed fma.rn.f32x2 (SASS FFMA2) takes one issue slot for two FMAs, and
+    // this stage is bound by issue slots, not by the FMA pipe (tools/micro/ffma2_bench.cu: FP32 work mixed with integer
+    // work runs 24 % faster packed).  The six slab distances of children J and J+1 are six FFMA2 instead of twelve FFMA.
+#define PT_CHILD2(J)                                                                                                  \
+  {                                                                                                                   \
+    float tnx0, tnx1, tny0, tny1, tnz0, tnz1, tfx0, tfx1, tfy0, tfy1, tfz0, tfz1;                                     \
+    fma2_bcast(tnx0, tnx1, byte_as_unit_float<J>(nx[h]), byte_as_unit_float<J + 1>(nx[h]), adjx, orgx);               \
+    fma2_bcast(tny0, tny1, byte_as_unit_float<J>(ny[h]), byte_as_unit_float<J + 1>(ny[h]), adjy, orgy);               \
+    fma2_bcast(tnz0, tnz1, byte_as_unit_float<J>(nz[h]), byte_as_unit_float<J + 1>(nz[h]), adjz, orgz);               \
+    fma2_bcast(tfx0, tfx1, byte_as_unit_float<J>(fx[h]), byte_as_unit_float<J + 1>(fx[h]), adjx, orgx);               \
+    fma2_bcast(tfy0, tfy1, byte_as_unit_float<J>(fy[h]), byte_as_unit_float<J + 1>(fy[h]), adjy, orgy);               \
+    fma2_bcast(tfz0, tfz1, byte_as_unit_float<J>(fz[h]), byte_as_unit_float<J + 1>(fz[h]), adjz, orgz);               \
+    /* fmaxf / fminf drop NaN operands (0 * inf from axis-parallel rays): the slab then does not constrain */         \
+    const float tn0 = fmaxf(fmaxf(tnx0, tny0), fmaxf(tnz0, s.t_min)), tf0 = fminf(fminf(tfx0, tfy0), fminf(tfz0, s.best_t)); \
+    const float tn1 = fmaxf(fmaxf(tnx1, tny1), fmaxf(tnz1, s.t_min)), tf1 = fminf(fminf(tfx1, tfy1), fminf(tfz1, s.best_t)); \
+    if (tn0 <= tf0) hitmask |= ((child_bits4 >> (8 * (J))) & 0xffu) << ((bit_index4 >> (8 * (J))) & 0xffu);           \
+    if (tn1 <= tf1) hitmask |= ((child_bits4 >> (8 * (J + 1))) & 0xffu) << ((bit_index4 >> (8 * (J + 1))) & 0xffu);   \
   }
-    PT_CHILD(0) PT_CHILD(1) PT_CHILD(2) PT_CHILD(3)
+    PT_CHILD2(0) PT_CHILD2(2)
 #undef PT_CHILD
   }
   s.ng.x = f2u(q1.x);
