@@ -111,6 +111,78 @@ PT_HD V3 mat_vector(const M4 &m, V3 v) {
   r.z = ((m.c0.z * v.x + m.c1.z * v.y) + m.c2.z * v.z) + m.c3.z * 0.0f;
   return r;
 }
+// ---- exact packed FP32 (sm_100a fma.rn.f32x2, SASS FFMA2: one issue slot for two IEEE operations) -------------------
+// The extend stage is bound by instruction issue, not by the FMA pipe (tools/micro/ffma2_bench.cu), so the unfused
+// multiplies and adds of the reference's arithmetic are issued two at a time:
+//     mul2: fma(a, b, -0.0) == RN(a * b)   (adding -0 changes no product, signed zeros included)
+//     add2: fma(a, 1.0, c)  == RN(a + c)   (a * 1 is exact)
+//     sub2: fma(b, -1.0, a) == RN(a - b)
+// each result rounded once, exactly like FMUL / FADD.  ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 even
+// under --fmad=false, so the operations are spelled as FMAs whose constants it cannot see (constant memory), which it
+// has no licence to merge.  The host build (hostsim) runs the scalar statements the packed ones replace.
+#if defined(__CUDACC__)
+__constant__ float kPackConst[4] = {-0.0f, 1.0f, -1.0f, 0.0f};
+struct F2 {
+  float x, y;
+};
+__device__ __forceinline__ F2 fma2(float ax, float ay, float bx, float by, float cx, float cy) {
+  F2 r;
+  asm("{ .reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%7}; fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0,%1}, rd; }"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(ax), "f"(ay), "f"(bx), "f"(by), "f"(cx), "f"(cy));
+  return r;
+}
+__device__ __forceinline__ F2 mul2(float ax, float ay, float bx, float by) { return fma2(ax, ay, bx, by, kPackConst[0], kPackConst[0]); }
+__device__ __forceinline__ F2 add2(float ax, float ay, float cx, float cy) { return fma2(ax, ay, kPackConst[1], kPackConst[1], cx, cy); }
+__device__ __forceinline__ F2 sub2(float ax, float ay, float bx, float by) { return fma2(bx, by, kPackConst[2], kPackConst[2], ax, ay); }
+#endif
+
+// mat_point(m, o) and mat_vector(m, d) of the same matrix in one go (what Cube::hit and Mesh::hit start with): x and y
+// of each product as packed pairs, the two z components as a third pair.  Same operations in the same order as the two
+// functions above, component by component.
+template <bool PACKED = true>
+PT_HD void mat_point_vector(const M4 &m, V3 o, V3 d, V3 &po, V3 &pd) {
+#if defined(__CUDA_ARCH__)
+  if (!PACKED) {  // k_extend_post waits on memory, not on issue slots: there the packing only adds moves
+    po = mat_point(m, o);
+    pd = mat_vector(m, d);
+    return;
+  }
+  F2 t, u;
+  t = mul2(m.c0.x, m.c0.y, o.x, o.x), u = mul2(m.c1.x, m.c1.y, o.y, o.y), t = add2(t.x, t.y, u.x, u.y);
+  u = mul2(m.c2.x, m.c2.y, o.z, o.z), t = add2(t.x, t.y, u.x, u.y);
+  t = add2(t.x, t.y, m.c3.x, m.c3.y);  // + c3 * 1.0f
+  po.x = t.x, po.y = t.y;
+  t = mul2(m.c0.x, m.c0.y, d.x, d.x), u = mul2(m.c1.x, m.c1.y, d.y, d.y), t = add2(t.x, t.y, u.x, u.y);
+  u = mul2(m.c2.x, m.c2.y, d.z, d.z), t = add2(t.x, t.y, u.x, u.y);
+  u = mul2(m.c3.x, m.c3.y, kPackConst[3], kPackConst[3]), t = add2(t.x, t.y, u.x, u.y);  // + c3 * 0.0f
+  pd.x = t.x, pd.y = t.y;
+  // (po.z, pd.z)
+  t = mul2(o.x, d.x, m.c0.z, m.c0.z), u = mul2(o.y, d.y, m.c1.z, m.c1.z), t = add2(t.x, t.y, u.x, u.y);
+  u = mul2(o.z, d.z, m.c2.z, m.c2.z), t = add2(t.x, t.y, u.x, u.y);
+  po.z = t.x + m.c3.z * 1.0f;
+  pd.z = t.y + m.c3.z * 0.0f;
+#else
+  po = mat_point(m, o);
+  pd = mat_vector(m, d);
+#endif
+}
+// mat_point alone, x and y packed
+PT_HD V3 mat_point_packed(const M4 &m, V3 p) {
+#if defined(__CUDA_ARCH__)
+  F2 t, u;
+  t = mul2(m.c0.x, m.c0.y, p.x, p.x), u = mul2(m.c1.x, m.c1.y, p.y, p.y), t = add2(t.x, t.y, u.x, u.y);
+  u = mul2(m.c2.x, m.c2.y, p.z, p.z), t = add2(t.x, t.y, u.x, u.y);
+  t = add2(t.x, t.y, m.c3.x, m.c3.y);
+  V3 r;
+  r.x = t.x, r.y = t.y;
+  r.z = ((m.c0.z * p.x + m.c1.z * p.y) + m.c2.z * p.z) + m.c3.z * 1.0f;
+  return r;
+#else
+  return mat_point(m, p);
+#endif
+}
+
 PT_HD V3 mat_t_vector(const M4 &m, V3 v) {
   V3 r;
   r.x = ((m.c0.x * v.x + m.c0.y * v.y) + m.c0.z * v.z) + m.c0.w * 0.0f;

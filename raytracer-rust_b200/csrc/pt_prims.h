@@ -95,11 +95,18 @@ PT_HD bool hit_quad(const float *f, const Ray &ray, float t_min, float t_max, Hi
 constexpr int32_t kCubeNormalPending = 2;
 PT_HD bool hit_cube_t(const float *f, const Ray &ray, float t_min, float t_max, Hit &h) {
   const M4 w2o = load_m4(f);
-  const V3 o = mat_point(w2o, ray.o);
-  const V3 d = mat_vector(w2o, ray.d);  // not renormalised (cube.rs:70-83)
+  V3 o, d;
+  mat_point_vector(w2o, ray.o, ray.d, o, d);  // d not renormalised (cube.rs:70-83)
   const float ix = 1.0f / d.x, iy = 1.0f / d.y, iz = 1.0f / d.z;
+#if defined(__CUDA_ARCH__)
+  // (-0.5 - o) * i and (0.5 - o) * i, x and y as packed pairs (pt_math.h: same roundings as the scalar statements)
+  const F2 a1 = sub2(-0.5f, -0.5f, o.x, o.y), a2 = sub2(0.5f, 0.5f, o.x, o.y);
+  const F2 m1 = mul2(a1.x, a1.y, ix, iy), m2 = mul2(a2.x, a2.y, ix, iy);
+  const float t1x = m1.x, t1y = m1.y, t2x = m2.x, t2y = m2.y;
+#else
   const float t1x = (-0.5f - o.x) * ix, t2x = (0.5f - o.x) * ix;
   const float t1y = (-0.5f - o.y) * iy, t2y = (0.5f - o.y) * iy;
+#endif
   const float t1z = (-0.5f - o.z) * iz, t2z = (0.5f - o.z) * iz;
   const float t_enter = fmaxf(fminf(t1x, t2x), fmaxf(fminf(t1y, t2y), fminf(t1z, t2z)));
   const float t_exit = fminf(fmaxf(t1x, t2x), fminf(fmaxf(t1y, t2y), fmaxf(t1z, t2z)));
@@ -108,7 +115,7 @@ PT_HD bool hit_cube_t(const float *f, const Ray &ray, float t_min, float t_max, 
   if (t_obj >= t_max || t_obj <= t_min || t_obj < kEps) return false;
   const V3 p = o + d * t_obj;
   const M4 o2w = load_m4(f + 16);
-  const V3 pw = mat_point(o2w, p);
+  const V3 pw = mat_point_packed(o2w, p);
   if (dot(pw - ray.o, ray.d) < 0.0f) return false;
   const float t_world = dot(pw - ray.o, ray.d);
   if (t_world < t_min || t_world > t_max) return false;  // closed interval (cube.rs:150)
@@ -152,11 +159,11 @@ PT_HD bool hit_cube(const float *f, const Ray &ray, float t_min, float t_max, Hi
 struct MeshRay {
   V3 o, d_raw, d;
 };
+template <bool PACKED = true>
 PT_HD MeshRay mesh_object_ray(const float *w2o_f, const Ray &ray) {
   const M4 w2o = load_m4(w2o_f);
   MeshRay r;
-  r.o = mat_point(w2o, ray.o);
-  r.d_raw = mat_vector(w2o, ray.d);
+  mat_point_vector<PACKED>(w2o, ray.o, ray.d, r.o, r.d_raw);
   r.d = normalized(normalized(r.d_raw));
   return r;
 }

@@ -310,7 +310,7 @@ __device__ __forceinline__ void stage_post(uint32_t seg, uint32_t n_seg, const D
       best.triangle = -1;
       bool improved = false;
       if (tri != 0xffffffffu) {
-        const MeshRay omr = mesh_object_ray(ob->f, ray);  // same inputs, same bits as in k_extend_pre
+        const MeshRay omr = mesh_object_ray<false>(ob->f, ray);  // same inputs, same bits as in k_extend_pre
         MeshHit mh;
         mh.t = res.x, mh.tri = tri, mh.order = 0u;
         Hit tmp;
