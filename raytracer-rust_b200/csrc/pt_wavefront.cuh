@@ -145,9 +145,12 @@ __device__ __forceinline__ void finish_hit(const DObject *objs, const Ray &ray, 
 
 // The object table is read by every lane for every ray; ray data streaming through L1 kept evicting it (the load of
 // `ob->type` alone was 12 % of k_extend_pre's stall samples), so each block stages it into shared memory once.
+// The stages are compiled twice, for the table in shared memory (kSharedObjs: loads are LDS, not generic LD) and, for
+// scenes with more than kSmemObjects objects, in global memory.
 constexpr int kSmemObjects = 24;
+template <bool kSharedObjs>
 __device__ __forceinline__ const DObject *stage_objects(const DScene &sc, DObject *s_objs) {
-  if (sc.n_objects > kSmemObjects) return sc.objects;
+  if (!kSharedObjs) return sc.objects;
   const uint4 *src = reinterpret_cast<const uint4 *>(sc.objects);
   uint4 *dst = reinterpret_cast<uint4 *>(s_objs);
   const int n16 = sc.n_objects * (int)(sizeof(DObject) / 16);
@@ -175,6 +178,7 @@ __device__ __forceinline__ void park_tasks(uint32_t *s_ntask, const TaskQ &tq, i
 // ---- the four stages, each written for ONE block working on ITS segment.  They are called either from the per-stage
 // kernels below (PTC_FLAG_TIMING / PTC_FLAG_COUNTERS / ptc_intersect: one launch per stage, CUDA events in between) or
 // back to back from the persistent kernel k_wavefront.
+template <bool kSharedObjs>
 __device__ __forceinline__ void stage_pre(uint32_t seg, uint32_t n_seg, const DScene &sc, const ExtendOut &out, const TaskQ &tq,
                                           float t_min, float t_max) {
   __shared__ uint32_t s_ntask;
@@ -182,7 +186,8 @@ __device__ __forceinline__ void stage_pre(uint32_t seg, uint32_t n_seg, const DS
   const uint32_t tid = threadIdx.x;
   const uint32_t n = out.b.cnt[seg], seg_base = seg * out.b.cap;
   if (tid == 0) s_ntask = 0;
-  const DObject *objs = stage_objects(sc, s_objs);
+  const DObject *objs = kSharedObjs ? s_objs : sc.objects;
+  stage_objects<kSharedObjs>(sc, s_objs);
   __syncthreads();
   for (uint32_t c0 = 0; c0 < n; c0 += (uint32_t)kBlock) {
     const uint32_t i = seg_base + c0 + tid;
@@ -275,6 +280,7 @@ __device__ __forceinline__ void stage_traverse(uint32_t seg, uint32_t n_seg, Ctl
   }
 }
 
+template <bool kSharedObjs>
 __device__ __forceinline__ void stage_post(uint32_t seg, uint32_t n_seg, const DScene &sc, const ExtendOut &out, const TaskQ &tq,
                                            int round, float t_min, float t_max) {
   __shared__ uint32_t s_ntask;
@@ -283,7 +289,8 @@ __device__ __forceinline__ void stage_post(uint32_t seg, uint32_t n_seg, const D
   const uint32_t n = tq.cnt[(uint32_t)round * n_seg + seg], seg_base = seg * out.b.cap;
   const int par = round & 1;
   if (tid == 0) s_ntask = 0;
-  const DObject *objs = stage_objects(sc, s_objs);
+  const DObject *objs = kSharedObjs ? s_objs : sc.objects;
+  stage_objects<kSharedObjs>(sc, s_objs);
   __syncthreads();
   for (uint32_t c0 = 0; c0 < n; c0 += (uint32_t)kBlock) {
     const uint32_t j = seg_base + c0 + tid;
@@ -582,7 +589,8 @@ __global__ void __launch_bounds__(kBlock, kSegPerSM) k_extend_pre(Ctl *ctl, SegR
     }
     ctl->n_live[sr.half] = 0;
   }
-  stage_pre(sr.seg0 + blockIdx.x, sr.n_seg, sc, out, tq, t_min, t_max);
+  if (sc.n_objects <= kSmemObjects) stage_pre<true>(sr.seg0 + blockIdx.x, sr.n_seg, sc, out, tq, t_min, t_max);
+  else stage_pre<false>(sr.seg0 + blockIdx.x, sr.n_seg, sc, out, tq, t_min, t_max);
 }
 template <bool COUNT>
 __global__ void __launch_bounds__(kBlock, kSegPerSM) k_traverse(Ctl *ctl, SegRange sr, DScene sc, TaskQ tq, int round, float t_min,
@@ -591,7 +599,8 @@ __global__ void __launch_bounds__(kBlock, kSegPerSM) k_traverse(Ctl *ctl, SegRan
 }
 __global__ void __launch_bounds__(kBlock, kSegPerSM) k_extend_post(SegRange sr, DScene sc, ExtendOut out, TaskQ tq, int round, float t_min,
                                                                    float t_max) {
-  stage_post(sr.seg0 + blockIdx.x, sr.n_seg, sc, out, tq, round, t_min, t_max);
+  if (sc.n_objects <= kSmemObjects) stage_post<true>(sr.seg0 + blockIdx.x, sr.n_seg, sc, out, tq, round, t_min, t_max);
+  else stage_post<false>(sr.seg0 + blockIdx.x, sr.n_seg, sc, out, tq, round, t_min, t_max);
 }
 __global__ void __launch_bounds__(kBlock, kSegPerSM) k_shade(Ctl *ctl, SegRange sr, DScene sc, RenderParams rp, Buffers b, float *accum) {
   stage_shade(sr.seg0 + blockIdx.x, sr.n_seg, sr.half, ctl, sc, rp, b, accum);

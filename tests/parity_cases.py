@@ -116,6 +116,35 @@ def check_random_rays_composite(kind, pt, n=200000, seed=1):
     return r, stats
 
 
+def check_many_objects(kind, pt, n=100000, seed=3):
+    """More objects than the kernels' shared-memory object table holds (24): the global-memory instantiation of the extend
+    stages, with two meshes among 40 analytic primitives so that parked rays resume in the middle of the list."""
+    s = pt.Scene()
+    m0 = s.add_material(pt.lambertian((0.5, 0.5, 0.5)))
+    rng = np.random.default_rng(seed)
+    for i in range(40):
+        pos = tuple(float(v) for v in rng.uniform(-60, 60, 3))
+        if i in (11, 29):
+            s.add_obj(os.path.join(SCENES, "RayTracingText.obj"), m0, scale=(0.6, 0.6, 0.6), rotation=(10.0 * i, 45, 0), position=pos)
+        elif i % 3 == 0:
+            s.add_sphere(pos, float(rng.uniform(3, 9)), m0)
+        elif i % 3 == 1:
+            s.add_cube(m0, scale=tuple(float(v) for v in rng.uniform(4, 14, 3)), rotation=tuple(float(v) for v in rng.uniform(0, 90, 3)),
+                       position=pos)
+        else:
+            s.add_quad(m0, scale=(float(rng.uniform(8, 20)), 1, float(rng.uniform(8, 20))), rotation=tuple(float(v) for v in rng.uniform(0, 180, 3)),
+                       position=pos)
+    s.set_camera((0, 0, 200), (0, 0, 0), (0, 1, 0), 50.0, 1.0)
+    s.set_settings(32, 32, 1, 4)
+    be = Backend(kind, pt, s)
+    o, d = rand_rays(rng, n, (0, 0, 0), 80.0)
+    got, _ = be.intersect(o, d)
+    want = OracleScene(s).intersect(pt, o, d)
+    r = assert_hits_identical(pt, got, want)
+    assert len(set(np.unique(want["object"]).tolist())) > 30
+    return r
+
+
 def check_mesh_build_facts(kind, pt):
     s = pt.load_scene_from_json(os.path.join(SCENES, "semesterbild.json"))
     be = Backend(kind, pt, s)

@@ -19,6 +19,10 @@ def test_random_rays_composite_scene(pt):
     pc.check_random_rays_composite(KIND, pt, n=400000)
 
 
+def test_many_objects(pt):
+    pc.check_many_objects(KIND, pt, n=200000)
+
+
 def test_mesh_build_facts(pt):
     pc.check_mesh_build_facts(KIND, pt)
 
