@@ -339,8 +339,8 @@ def main():
                               "peak_source": f"{sms} SMs x 128 lanes x {sm_mhz:.0f} MHz sampled under load",
                               "ncu": ncu_kernels,
                               "note": "algorithmic count with FMA = 1 and no divergence; what the kernels EXECUTE (unfused IEEE "
-                                      "arithmetic for bit-exact hit records, incoherent rays) keeps the issue slots busy 76 % / 66 % / "
-                                      "42 % of the time in pre / traverse / post (ncu, profiles/r1_v3_stages_ncu_summary.txt)"},
+                                      "arithmetic for bit-exact hit records, incoherent rays) keeps the issue slots busy 74 % / 60 % / "
+                                      "47 % of the time in pre / traverse / post (ncu, profiles/r1_v4_stages_ncu_summary.txt)"},
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(pt, scene)
