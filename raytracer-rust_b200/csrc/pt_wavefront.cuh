@@ -175,9 +175,7 @@ __device__ __forceinline__ void park_tasks(uint32_t *s_ntask, const TaskQ &tq, i
   }
 }
 
-// ---- the four stages, each written for ONE block working on ITS segment.  They are called either from the per-stage
-// kernels below (PTC_FLAG_TIMING / PTC_FLAG_COUNTERS / ptc_intersect: one launch per stage, CUDA events in between) or
-// back to back from the persistent kernel k_wavefront.
+// ---- the four stages, each written for ONE block working on ITS segment; the per-stage kernels below call them.
 template <bool kSharedObjs>
 __device__ __forceinline__ void stage_pre(uint32_t seg, uint32_t n_seg, const DScene &sc, const ExtendOut &out, const TaskQ &tq,
                                           float t_min, float t_max) {
