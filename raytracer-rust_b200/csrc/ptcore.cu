@@ -311,7 +311,8 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
     std::deque<int> pending;
     int ring_next = 0;
     uint64_t it = 0;
-    const int check_every = 4;
+    int check_every = 4;  // 1 once a snapshot shows the path supply exhausted: the drain's launches are cheap, running ahead of
+                          // the device by up to kRing x 4 empty iterations at the end of every render is not
     bool finished = false;
     while (!finished) {
       run_extend();
@@ -338,6 +339,7 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
             finished = true;
             break;
           }
+          if (s->h_ctl[o].next_path >= s->h_ctl[o].total_paths) check_every = 1;
         }
       }
     }
