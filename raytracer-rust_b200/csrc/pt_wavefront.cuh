@@ -576,9 +576,20 @@ __device__ __forceinline__ uint32_t stage_shade(uint32_t seg, uint32_t n_seg, ui
   return w;
 }
 
+// Programmatic dependent launch (sm_90+): the host marks every stage launch of a render as allowed to start before its
+// predecessor in the stream has drained; a kernel first lets ITS successor be scheduled, then waits until the
+// predecessor has completed and its writes are visible.  What overlaps is the launch latency and block scheduling of
+// four dependent launches per iteration (~3 us each, a fifth of a drain iteration); every data access stays behind the
+// wait.  Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // ---- per-stage kernels: one block per segment --------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock, kSegPerSM) k_extend_pre(Ctl *ctl, SegRange sr, DScene sc, ExtendOut out, TaskQ tq, float t_min,
                                                                   float t_max) {
+  pdl_prologue();
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // iteration bookkeeping (the previous shade has finished: stream order)
     const uint32_t live = ctl->n_live[sr.half];
     if (live) {
@@ -593,14 +604,17 @@ __global__ void __launch_bounds__(kBlock, kSegPerSM) k_extend_pre(Ctl *ctl, SegR
 template <bool COUNT>
 __global__ void __launch_bounds__(kBlock, kSegPerSM) k_traverse(Ctl *ctl, SegRange sr, DScene sc, TaskQ tq, int round, float t_min,
                                                                 uint32_t cap, uint32_t refill_lanes) {
+  pdl_prologue();
   stage_traverse<COUNT>(sr.seg0 + blockIdx.x, sr.n_seg, ctl, sc, tq, round, t_min, cap, refill_lanes);
 }
 __global__ void __launch_bounds__(kBlock, kSegPerSM) k_extend_post(SegRange sr, DScene sc, ExtendOut out, TaskQ tq, int round, float t_min,
                                                                    float t_max) {
+  pdl_prologue();
   if (sc.n_objects <= kSmemObjects) stage_post<true>(sr.seg0 + blockIdx.x, sr.n_seg, sc, out, tq, round, t_min, t_max);
   else stage_post<false>(sr.seg0 + blockIdx.x, sr.n_seg, sc, out, tq, round, t_min, t_max);
 }
 __global__ void __launch_bounds__(kBlock, kSegPerSM) k_shade(Ctl *ctl, SegRange sr, DScene sc, RenderParams rp, Buffers b, float *accum) {
+  pdl_prologue();
   stage_shade(sr.seg0 + blockIdx.x, sr.n_seg, sr.half, ctl, sc, rp, b, accum);
 }
 

@@ -161,6 +161,20 @@ namespace {
 
 enum Stage { ST_PRE = 0, ST_TRAVERSE, ST_POST, ST_SHADE, ST_COUNT };
 
+// One stage launch of the render loop: `segments` blocks of kBlock threads, optionally as a programmatic dependent launch
+// (pt_wavefront.cuh: pdl_prologue).
+template <typename... KArgs, typename... Args>
+void launch_stage(bool pdl, cudaStream_t stream, uint32_t segments, void (*kernel)(KArgs...), Args &&...args) {
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(segments), cfg.blockDim = dim3(kBlock), cfg.dynamicSmemBytes = 0, cfg.stream = stream;
+  cfg.attrs = pdl ? &attr : nullptr, cfg.numAttrs = pdl ? 1 : 0;
+  CK(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
+}
+
 // One extend pass over ALL segments on one stream (ptc_intersect) = pre, then (traverse, post) once per mesh object a ray
 // can meet.  Returns the number of launches.
 int launch_extend(cudaStream_t stream, uint32_t segments, int rounds, Ctl *ctl, const DScene &ds, const ExtendOut &eo, const TaskQ &tq,
@@ -285,25 +299,29 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
   uint64_t launches = 0;
   static const uint32_t refill = getenv("PTC_REFILL") ? (uint32_t)atoi(getenv("PTC_REFILL")) : kRefillLanes;
   auto is_done = [](const Ctl &c) { return c.n_live[0] == 0 && c.next_path >= c.total_paths; };
+  // programmatic dependent launches, unless the per-stage events are wanted (they would sit between the launches) or
+  // PTC_PDL=0
+  static const bool pdl_on = getenv("PTC_PDL") ? atoi(getenv("PTC_PDL")) != 0 : true;
+  const bool pdl = pdl_on && !timing;
   if (init.total_paths != 0) {
     const SegRange sr{0u, segments, 0u};
     int flip = 0;  // the ray set the extend stages read
     auto run_extend = [&]() {
       const ExtendOut eo{bufs[flip], nullptr};
       if (timing) mark(ST_PRE);
-      k_extend_pre<<<segments, kBlock, 0, stream>>>(s->d_ctl.p, sr, s->ds, eo, tq, kEps, INFINITY);  // renderer.rs:24
+      launch_stage(pdl, stream, segments, k_extend_pre, s->d_ctl.p, sr, s->ds, eo, tq, kEps, INFINITY);  // renderer.rs:24
       for (int r = 0; r < rounds; r++) {
         if (timing) mark(ST_TRAVERSE);
-        if (counters) k_traverse<true><<<segments, kBlock, 0, stream>>>(s->d_ctl.p, sr, s->ds, tq, r, kEps, eo.b.cap, refill);
-        else k_traverse<false><<<segments, kBlock, 0, stream>>>(s->d_ctl.p, sr, s->ds, tq, r, kEps, eo.b.cap, refill);
+        if (counters) launch_stage(pdl, stream, segments, k_traverse<true>, s->d_ctl.p, sr, s->ds, tq, r, kEps, eo.b.cap, refill);
+        else launch_stage(pdl, stream, segments, k_traverse<false>, s->d_ctl.p, sr, s->ds, tq, r, kEps, eo.b.cap, refill);
         if (timing) mark(ST_POST);
-        k_extend_post<<<segments, kBlock, 0, stream>>>(sr, s->ds, eo, tq, r, kEps, INFINITY);
+        launch_stage(pdl, stream, segments, k_extend_post, sr, s->ds, eo, tq, r, kEps, INFINITY);
       }
       launches += 1 + 2 * (uint64_t)rounds;
     };
     auto run_shade = [&]() {  // reads set `flip`, writes the other one, which the next extend then reads
       if (timing) mark(ST_SHADE);
-      k_shade<<<segments, kBlock, 0, stream>>>(s->d_ctl.p, sr, s->ds, rp, bufs[flip], d_accum);
+      launch_stage(pdl, stream, segments, k_shade, s->d_ctl.p, sr, s->ds, rp, bufs[flip], d_accum);
       launches += 1;
       flip ^= 1;
     };
