@@ -282,7 +282,90 @@ QFrame make_frame(const Box3 &box) {
   return f;
 }
 
+// Which binary subtrees become the (up to eight) children of a wide node.  The greedy rule (open the child with the
+// largest area until there are eight) leaves the bottom of the tree badly filled — 4.3 children per node and 1.8
+// triangles per leaf on the 2 M-triangle mesh — and the traversal pays the full ~330 instructions of a node step
+// whatever the fill.  The plan below is the dynamic programme of Ylitie, Karras & Laine 2017 (section 4.2) over the
+// binary SAH tree:  C(n, i) = cheapest way to turn the subtree of n into at most i children of some wide node,
+//     C(n, 1) = min( area(n) * tris(n) * c_t          if tris(n) <= 3   (the whole subtree as ONE leaf),
+//                    area(n) * c_n + D(n, 8) )                          (an inner wide node with up to 8 children)
+//     C(n, i) = min( D(n, i), C(n, i - 1) ),   D(n, j) = min_k C(left, k) + C(right, j - k).
+struct CollapsePlan {
+  std::vector<float> cost;     // [n * 8 + i - 1], i = 1..7
+  std::vector<uint8_t> split;  // [n * 8 + i - 1]: triangles/children given to the LEFT subtree for D(n, i), 0 = "same as i - 1";
+                               // entry i = 8 (index 7): the split of the node's own eight slots
+  std::vector<uint8_t> leaf;   // C(n, 1) is realised as a leaf
+  bool greedy = false;
+};
+CollapsePlan plan_collapse(const std::vector<B2> &b2, int32_t root) {
+  CollapsePlan p;
+  p.greedy = getenv("PTC_COLLAPSE") && !strcmp(getenv("PTC_COLLAPSE"), "greedy");
+  p.leaf.assign(b2.size(), 0);
+  if (p.greedy) return p;
+  const double c_t = 1.0, c_n = getenv("PTC_SAH_CN") ? atof(getenv("PTC_SAH_CN")) : 1.8;  // ncu: a node step costs ~1.8 triangle tests per lane
+  p.cost.assign(b2.size() * 8, 0.0f);
+  p.split.assign(b2.size() * 8, 0);
+  std::vector<int32_t> order;  // post-order
+  {
+    std::vector<int32_t> st{root};
+    while (!st.empty()) {
+      const int32_t n = st.back();
+      st.pop_back();
+      order.push_back(n);
+      if (b2[n].left >= 0) st.push_back(b2[n].left), st.push_back(b2[n].right);
+    }
+    std::reverse(order.begin(), order.end());
+  }
+  for (const int32_t n : order) {
+    const B2 &nd = b2[n];
+    const double area = nd.box.area();
+    float *C = &p.cost[(size_t)n * 8];
+    uint8_t *S = &p.split[(size_t)n * 8];
+    if (nd.left < 0) {
+      for (int i = 0; i < 8; i++) C[i] = (float)(area * nd.count * c_t);
+      p.leaf[n] = 1;
+      continue;
+    }
+    const float *L = &p.cost[(size_t)nd.left * 8], *R = &p.cost[(size_t)nd.right * 8];
+    double D[9];
+    uint8_t K[9];
+    for (int j = 2; j <= 8; j++) {
+      D[j] = DBL_MAX, K[j] = 1;
+      for (int k = 1; k < j; k++) {
+        const double v = (double)L[k - 1] + (double)R[j - k - 1];
+        if (v < D[j]) D[j] = v, K[j] = (uint8_t)k;
+      }
+    }
+    const double c_leaf = nd.count <= kLeafMax ? area * nd.count * c_t : DBL_MAX;
+    const double c_inner = area * c_n + D[8];
+    p.leaf[n] = c_leaf <= c_inner ? 1 : 0;
+    C[0] = (float)std::min(c_leaf, c_inner);
+    S[7] = K[8];
+    for (int i = 2; i <= 7; i++) {
+      if (D[i] < (double)C[i - 2]) C[i - 1] = (float)D[i], S[i - 1] = K[i];
+      else C[i - 1] = C[i - 2], S[i - 1] = 0;
+    }
+  }
+  return p;
+}
+// the children the plan gives to `slots` slots of a wide node for the subtree of n
+void plan_children(const std::vector<B2> &b2, const CollapsePlan &p, int32_t n, int slots, int32_t *ch, int &nch) {
+  if (b2[n].left < 0 || slots == 1) {
+    ch[nch++] = n;
+    return;
+  }
+  const int k = p.split[(size_t)n * 8 + slots - 1];
+  if (k == 0) {
+    plan_children(b2, p, n, slots - 1, ch, nch);
+    return;
+  }
+  plan_children(b2, p, b2[n].left, k, ch, nch);
+  plan_children(b2, p, b2[n].right, slots - k, ch, nch);
+}
+
 void collapse(const std::vector<B2> &b2, int32_t root, const int32_t *prim, const int32_t *live_ids, MeshBuild &m) {
+  const CollapsePlan plan = plan_collapse(b2, root);
+  auto is_leaf = [&](int32_t c) { return plan.greedy ? b2[c].left < 0 : plan.leaf[c] != 0; };
   struct Item {
     int32_t b2, wide, depth;
   };
@@ -298,13 +381,17 @@ void collapse(const std::vector<B2> &b2, int32_t root, const int32_t *prim, cons
     const B2 &n = b2[it.b2];
     int32_t ch[8];
     int nch = 0;
-    if (n.left < 0) {
+    if (is_leaf(it.b2)) {
       ch[nch++] = it.b2;
+    } else if (!plan.greedy) {
+      const int k = plan.split[(size_t)it.b2 * 8 + 7];
+      plan_children(b2, plan, n.left, k, ch, nch);
+      plan_children(b2, plan, n.right, 8 - k, ch, nch);
     } else {
       ch[nch++] = n.left;
       ch[nch++] = n.right;
     }
-    while (nch < 8) {  // open the inner child with the largest surface area
+    while (plan.greedy && nch < 8) {  // open the inner child with the largest surface area
       int pick = -1;
       double pa = -1.0;
       for (int i = 0; i < nch; i++)
@@ -379,7 +466,7 @@ void collapse(const std::vector<B2> &b2, int32_t root, const int32_t *prim, cons
       const int32_t c = slot_child[s];
       if (c < 0) continue;
       const B2 &cn = b2[c];
-      if (cn.left >= 0) {
+      if (!is_leaf(c)) {
         imask |= 1u << s;
         meta[s] = (uint8_t)(0x20 | (24 + s));
         queue.push_back({c, (int32_t)(child_base + n_inner), it.depth + 1});
@@ -530,6 +617,22 @@ void build_mesh(MeshBuild &m, int threads) {
   // ---- step 3
   collapse(sc.nodes, root, prim.data(), live_ids.data(), m);
   m.built = true;
+  if (timing) {
+    size_t inner = 0, leaf = 0, tris = 0;
+    for (const Node8 &nd : m.nodes) {
+      uint32_t w[2];
+      memcpy(w, &nd.q[1].z, 8);
+      for (int s8 = 0; s8 < 8; s8++) {
+        const uint32_t meta = (w[s8 >> 2] >> (8 * (s8 & 3))) & 0xffu;
+        if (meta == 0) continue;
+        if ((meta & 0x30u) == 0x20u && (meta & 0x1fu) >= 24) inner++;
+        else leaf++, tris += (meta >> 5) == 1 ? 1 : ((meta >> 5) == 3 ? 2 : 3);
+      }
+    }
+    fprintf(stderr, "[pt_build] wide nodes %zu: %.2f children per node (%.2f inner + %.2f leaves), %.2f triangles per leaf, depth %d\n",
+            m.nodes.size(), (double)(inner + leaf) / m.nodes.size(), (double)inner / m.nodes.size(), (double)leaf / m.nodes.size(),
+            (double)tris / std::max<size_t>(1, leaf), m.wide_depth);
+  }
   if (timing)
     fprintf(stderr, "[pt_build] %lld triangles (%lld live), %d threads: reference-BVH restatement %.0f ms, binned SAH %.0f ms, "
                     "8-wide collapse + quantisation %.0f ms; %zu wide nodes\n",

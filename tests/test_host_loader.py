@@ -285,11 +285,23 @@ def test_reference_bvh_restatement_radix_equals_stable_sort(scenes_dir):
         "        print(info.ref_nodes, info.ref_leaves, info.ref_depth, info.live_triangles, hashlib.md5(dead.tobytes()).hexdigest(),\n"
         "              hashlib.md5(order.tobytes()).hexdigest())\n"
     ) % (os.path.dirname(scenes_dir), os.path.join(os.path.dirname(scenes_dir), "tests"), os.path.join(scenes_dir, "teapot", "scene.json"))
+    prog += (
+        "import numpy as np\n"
+        "rng = np.random.default_rng(5)\n"
+        "o = rng.uniform(-30, 30, (20000, 3)).astype(np.float32); d = rng.normal(size=(20000, 3)).astype(np.float32)\n"
+        "d /= np.linalg.norm(d, axis=1, keepdims=True)\n"
+        "hits, st = sim.intersect(pt, o, d)\n"
+        "print(hashlib.md5(hits.tobytes()).hexdigest(), int((hits['object'] >= 0).sum()))\n"
+    )
     outs = []
-    for force in ("", "1"):
+    for var, val in (("", ""), ("PTC_REF_STABLE_SORT", "1"), ("PTC_COLLAPSE", "greedy")):
         env = dict(os.environ)
         env.pop("PTC_REF_STABLE_SORT", None)
-        if force:
-            env["PTC_REF_STABLE_SORT"] = force
+        env.pop("PTC_COLLAPSE", None)
+        if var:
+            env[var] = val
         outs.append(subprocess.run([sys.executable, "-c", prog], env=env, capture_output=True, text=True, check=True).stdout)
-    assert outs[0] == outs[1] and len(outs[0].splitlines()) == 2
+    # same reference-BVH facts with either sort, and the same hit records whichever way the wide tree was collapsed
+    # (the dynamic-programme collapse is the default, PTC_COLLAPSE=greedy the first version)
+    assert outs[0] == outs[1] == outs[2] and len(outs[0].splitlines()) == 3
+    assert int(outs[0].splitlines()[2].split()[1]) > 1000
