@@ -1,6 +1,6 @@
 # Build everything in-tree (the .so files are git-ignored but travel to the GPU box with the snapshot).
 #   libptcore.so   product: CUDA kernels for sm_100a + C ABI (include/ptcore.h).  No CPU fallback inside.
-#   libpthost.so   C++ stand-in for the reference's Rust host side (include/pthost.h); links libptcore.
+#   libpthost.so   C++ stand-in for the reference's Rust host side (include/pthost.h); binds libptcore at first use (dlopen).
 #   liboracle.so   TEST INFRASTRUCTURE: CPU restatement of the reference (oracle/).
 #   libhostsim.so  TEST INFRASTRUCTURE: the device headers compiled by g++ (tests/hostsim/).
 NVCC ?= nvcc
@@ -20,8 +20,8 @@ all: $(PKG)/libptcore.so $(PKG)/libpthost.so oracle/liboracle.so tests/hostsim/l
 $(PKG)/libptcore.so: $(CSRC)/ptcore.cu $(CSRC)/pt_build.cpp $(HDRS)
 	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(CSRC)/ptcore.cu $(CSRC)/pt_build.cpp -ldl
 
-$(PKG)/libpthost.so: $(PKG)/host/pthost.cpp $(PKG)/host/json.hpp $(PKG)/libptcore.so include/pthost.h include/ptcore.h
-	$(CXX) $(CXXFLAGS) -shared -o $@ $(PKG)/host/pthost.cpp -L$(PKG) -lptcore -lz -Wl,-rpath,'$$ORIGIN'
+$(PKG)/libpthost.so: $(PKG)/host/pthost.cpp $(PKG)/host/json.hpp include/pthost.h include/ptcore.h
+	$(CXX) $(CXXFLAGS) -shared -o $@ $(PKG)/host/pthost.cpp -lz -ldl
 
 oracle/liboracle.so: oracle/oracle.cpp oracle/oracle.h
 	$(MAKE) -C oracle

@@ -77,13 +77,15 @@ typedef struct ptc_render_settings {
   int32_t sample_end;
   int32_t tile_mod;     /* pixel sharding: only 32x32 tiles with tile_index % tile_mod == tile_rem; 0 = all */
   int32_t tile_rem;
-  int32_t pool_paths;   /* path-pool slots; 0 = default (up to 1<<22, less for small renders) */
+  int32_t pool_paths;   /* path-pool slots; 0 = default (up to 1<<23, less for small renders) */
   int32_t flags;        /* PTC_FLAG_* */
 } ptc_render_settings;
 
 enum {
   PTC_FLAG_COUNTERS = 1, /* run the instrumented extend kernel: fills nodes_visited / tris_tested (slower) */
-  PTC_FLAG_TIMING = 2    /* record CUDA events around every extend / shade launch: fills extend_ms / shade_ms */
+  PTC_FLAG_TIMING = 2,   /* record CUDA events around every extend / shade launch: fills extend_ms / shade_ms */
+  PTC_FLAG_NO_TAIL = 4   /* keep the staged kernels to the last ray: never finish the drain's last few thousand rays inside
+                            the shade kernel (same image and ray count either way; for tests and measurements) */
 };
 
 /* HitRecord (src/hittable.rs:10-16) plus the ids the parity bar is stated on. */
@@ -110,7 +112,7 @@ typedef struct ptc_stats {
   uint64_t tris_tested;    /* triangles tested        (only with PTC_FLAG_COUNTERS) */
   uint64_t mesh_rays;      /* ray x mesh-instance traversals (only with PTC_FLAG_COUNTERS) */
   double pre_ms, traverse_ms, post_ms; /* the three kernels of the extend stage (PTC_FLAG_TIMING); extend_ms = their sum */
-  double regen_ms;         /* k_advance + k_generate (PTC_FLAG_TIMING) */
+  double regen_ms;         /* always 0: path regeneration is part of the shade kernel (kept for ABI v1 layout) */
 } ptc_stats;
 
 typedef struct ptc_mesh_info {
@@ -164,7 +166,8 @@ int ptc_render(ptc_scene *, const ptc_camera *, const ptc_render_settings *, flo
  * the Vec<u32> the reference returns.  The film is resolved on the device; only W*H*4 bytes cross PCIe. */
 int ptc_render_u32(ptc_scene *, const ptc_camera *, const ptc_render_settings *, uint32_t *out_u32, ptc_stats *stats);
 /* Same, device-resident: ADDS this call's radiance sum (not divided by spp) into d_accum (W*H*3 floats in
- * device memory of the scene's device), ordered on `cuda_stream` (a cudaStream_t, NULL = default stream).
+ * device memory of the scene's device), ordered on `cuda_stream` (a cudaStream_t; NULL = the legacy default stream,
+ * so work the caller queued on stream 0 — zeroing d_accum, waiting for a collective — is ordered before the render).
  * Returns after the work is enqueued AND finished (the wavefront loop polls its queue counters). */
 int ptc_render_accumulate(ptc_scene *, const ptc_camera *, const ptc_render_settings *, float *d_accum,
                           void *cuda_stream, ptc_stats *stats);

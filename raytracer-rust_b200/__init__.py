@@ -21,7 +21,7 @@ REPO_ROOT = os.path.dirname(_HERE)
 PTC_OK, PTC_E_INVALID, PTC_E_CUDA, PTC_E_NOMEM, PTC_E_STATE = 0, -1, -2, -3, -4
 MAT_LAMBERT, MAT_LAMBERT_CHECKER, MAT_METAL, MAT_DIELECTRIC, MAT_EMISSIVE, MAT_PLASTIC, MAT_ROUGH_CONDUCTOR, MAT_NULL = range(8)
 DIST_GGX, DIST_BECKMANN = 0, 1
-FLAG_COUNTERS, FLAG_TIMING = 1, 2
+FLAG_COUNTERS, FLAG_TIMING, FLAG_NO_TAIL = 1, 2, 4
 LOAD_INFINITE_SPHERE_SKY, LOAD_WO3_STRIDE16, LOAD_SKIP_UNKNOWN = 1, 2, 4
 OBJ_SPHERE, OBJ_PLANE, OBJ_QUAD, OBJ_CUBE, OBJ_MESH = range(5)
 
@@ -160,8 +160,7 @@ def host():
     global _host
     if _host is not None:
         return _host
-    core()
-    p = host_path()
+    p = host_path()  # binds libptcore.so itself, when a scene is first handed to the core (pth_build_ptc_scene)
     if not os.path.exists(p):
         raise ImportError(f"{p} is missing: build it first (`make`, or __graft_entry__.build())")
     L = C.CDLL(p)

@@ -16,7 +16,7 @@
 //
 // Consequences: no global compaction, no global queue cursor — the only same-address global atomics left are one
 // `next_path` reservation and one `n_live` add per block and iteration (per-warp atomics on single counters were 16-56 %
-// of the stall samples of the previous design, profiles/r1_v3_*); ray state is single-buffered; each block's working
+// of the stall samples of the previous design, profiles/r1_v3_*); the ray arrays are ping-ponged between two sets (k_shade reads one, writes the other); each block's working
 // set stays in its own slice of memory; when the path supply runs out all segments drain together, so the tail needs
 // no repacking either.  (A persistent one-kernel variant and a two-stream variant of this loop were measured slower on
 // B200 and removed; DESIGN.md section 5 keeps the numbers.)
@@ -36,6 +36,7 @@ using namespace pt;
 
 constexpr int kBlock = 256;    // threads per block of every stage kernel
 constexpr int kSegPerSM = 4;   // segments (= resident blocks) per SM: 4 x 256 threads x <= 64 registers
+constexpr uint32_t kTailRays = 1u << 16;  // default of RenderParams::tail_rays
 constexpr uint32_t kRefillLanes = 8;  // a traversal warp fetches new tasks once this many lanes are idle
 
 // Device-side control block of one render
@@ -46,6 +47,8 @@ struct Ctl {
   unsigned long long nodes, tris, mesh_rays;  // PTC_FLAG_COUNTERS
   uint32_t n_live[2];      // rays alive after the last shade (sum of the segment counts), per half-wavefront
   uint32_t iterations[2];  // per half-wavefront
+  uint32_t prev_live;      // rays that entered the iteration in flight (written by k_extend_pre, read by k_shade's tail rule)
+  uint32_t tail_blocks;    // blocks that finished their segment inside k_shade (statistics)
 };
 
 // A kernel launch covers segments [seg0, seg0 + gridDim.x).
@@ -62,6 +65,8 @@ struct RenderParams {
   int32_t sample_begin, n_samples;
   int32_t tiles_x, n_my_tiles, tile_mod, tile_rem;
   uint32_t row_mult;  // odd, coprime with n_my_tiles: scatters consecutive 32-pixel rows over the image (see k_shade)
+  uint32_t tail_rays;  // once the path supply is exhausted and at most this many rays are in flight, every block finishes its
+                       // own segment inside k_shade (stage_tail); 0 = never
   uint64_t seed;
 };
 
@@ -337,6 +342,62 @@ __device__ __forceinline__ void stage_post(uint32_t seg, uint32_t n_seg, const D
   if (tid == 0) tq.cnt[(uint32_t)(round + 1) * n_seg + seg] = s_ntask;
 }
 
+// ---- the drain's tail ---------------------------------------------------------------------------------------------
+// Once the path supply is exhausted every iteration carries fewer rays than the one before, and the last ~25 of a
+// depth-30 render carry a few thousand: four dependent launches of 592 blocks each, ~65 us per iteration, for work that
+// would fit a handful of warps — 2 ms of a C2 frame, and the part that does not shrink when the frame is split over
+// eight GPUs.  When at most `tail_rays` rays entered the iteration in flight, every block therefore finishes the
+// survivors of ITS segment right here: one thread per ray runs trace_ray's loop (renderer.rs:19-65) to the end with the
+// straight-line closest hit (scene_hit: the same device functions, the same bits as the staged kernels) and the same
+// Philox keys (pixel, sample, bounce), so the image and the ray count are those of the staged iterations.  The cost is
+// the longest remaining path's dependent chain (~10 us per bounce) instead of one iteration per bounce.
+__device__ __noinline__ void stage_tail(uint32_t seg_base, uint32_t n, Ctl *ctl, const DScene &sc, const RenderParams &rp, const Buffers &b,
+                                        float *accum) {
+  unsigned long long my_rays = 0;
+  for (uint32_t j = threadIdx.x; j < n; j += (uint32_t)kBlock) {
+    const float4 o4 = b.nray_o[seg_base + j], d4 = b.nray_d[seg_base + j], b4 = b.nbeta[seg_base + j];
+    const uint32_t pixel = f2u(o4.w), sample = f2u(d4.w);
+    uint32_t bounce = f2u(b4.w);
+    Ray ray{v3(o4.x, o4.y, o4.z), v3(d4.x, d4.y, d4.z)};
+    V3 beta = v3(b4.x, b4.y, b4.z);
+    V3 radiance = v3(0, 0, 0);
+    bool add = false;
+    for (;;) {
+      my_rays++;
+      Hit best;
+      if (!scene_hit<false>(sc, ray, kEps, INFINITY, best, nullptr)) {  // renderer.rs:24, 38-63
+        radiance = radiance + beta * sky_color(sc, ray.d);
+        add = true;
+        break;
+      }
+      const DMaterial m = sc.materials[best.material];
+      const V3 e = mat_emitted(m);
+      if (e.x != 0.0f || e.y != 0.0f || e.z != 0.0f) {
+        radiance = radiance + beta * e;
+        add = true;
+      }
+      const Uniforms4 u = philox_uniforms(rp.seed, pixel, sample, bounce, 0u);
+      Ray sc_ray;
+      V3 att;
+      if (!mat_scatter(m, ray.d, v3(best.px, best.py, best.pz), v3(best.nx, best.ny, best.nz), best.front_face != 0, u.u, sc_ray, att)) break;
+      if (bounce + 1u >= (uint32_t)rp.max_depth) break;  // trace_ray(scattered, 0) is black (renderer.rs:20-22)
+      beta = beta * att;
+      ray = sc_ray;
+      bounce++;
+    }
+    if (add) {
+      float *px = accum + (size_t)pixel * 3;
+      atomicAdd(px + 0, radiance.x);
+      atomicAdd(px + 1, radiance.y);
+      atomicAdd(px + 2, radiance.z);
+    }
+  }
+  // one global atomic per warp (a block has at most a few hundred rays here)
+  for (int d = 16; d > 0; d >>= 1) my_rays += __shfl_xor_sync(0xffffffffu, my_rays, d);
+  if ((threadIdx.x & 31u) == 0u && my_rays) atomicAdd(&ctl->rays, my_rays);
+  if (threadIdx.x == 0) atomicAdd(&ctl->tail_blocks, 1u);
+}
+
 constexpr int kShadeClasses = 10;  // 0 = miss, 1 + material type (8 types), 9 = no ray (tail of the last window)
 constexpr int kShadeWindow = 2048;                   // rays one block sorts together
 constexpr int kShadeGroups = kShadeWindow / kBlock;  // 32-ray groups each warp shades per window
@@ -569,12 +630,26 @@ __device__ __forceinline__ uint32_t stage_shade(uint32_t seg, uint32_t n_seg, ui
     __syncthreads();
     if (!again) break;
   }
+  // the tail rule (see stage_tail), decided by one thread so that the whole block agrees: prev_live was written by the
+  // k_extend_pre of this iteration, next_path only grows
+  if (rp.tail_rays != 0u) {
+    if (tid == 0) {
+      const uint32_t in_flight = ctl->prev_live;
+      s_more = (w != 0u && in_flight != 0u && in_flight <= rp.tail_rays && ctl->next_path >= ctl->total_paths) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_more != 0u) {
+      stage_tail(seg_base, w, ctl, sc, rp, b, accum);
+      w = 0u;
+    }
+  }
   if (tid == 0) {
     b.cnt[seg] = w;
     if (w) atomicAdd(&ctl->n_live[half], w);
   }
   return w;
 }
+
 
 // Programmatic dependent launch (sm_90+): the host marks every stage launch of a render as allowed to start before its
 // predecessor in the stream has drained; a kernel first lets ITS successor be scheduled, then waits until the
@@ -596,6 +671,7 @@ __global__ void __launch_bounds__(kBlock, kSegPerSM) k_extend_pre(Ctl *ctl, SegR
       atomicAdd(&ctl->rays, (unsigned long long)live);
       ctl->iterations[sr.half]++;
     }
+    ctl->prev_live = live;
     ctl->n_live[sr.half] = 0;
   }
   if (sc.n_objects <= kSmemObjects) stage_pre<true>(sr.seg0 + blockIdx.x, sr.n_seg, sc, out, tq, t_min, t_max);

@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <chrono>
 #include <memory>
+#include <mutex>
 #include <thread>
 #include <cstdio>
 #include <cstdlib>
@@ -244,6 +245,11 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
   rp.n_my_tiles = tile_rem < n_tiles ? (n_tiles - tile_rem + tile_mod - 1) / tile_mod : 0;
   rp.tile_mod = tile_mod, rp.tile_rem = tile_rem;
   rp.seed = st->seed;
+  {  // the drain's tail (pt_wavefront.cuh: stage_tail); PTC_TAIL_RAYS overrides the threshold, 0 disables
+    const char *tail_s = getenv("PTC_TAIL_RAYS");  // read per call: measurements sweep it inside one process
+    const long tail_env = tail_s ? atol(tail_s) : -1;
+    rp.tail_rays = (st->flags & PTC_FLAG_NO_TAIL) ? 0u : (tail_env >= 0 ? (uint32_t)tail_env : kTailRays);
+  }
   {  // odd multiplier coprime with the number of 32-pixel rows (= n_my_tiles * 32): a bijection on row indices
     auto gcd = [](uint64_t a, uint64_t b) {
       while (b) {
@@ -499,6 +505,7 @@ struct NcclApi {
   ncclResult_t (*GetVersion)(int *) = nullptr;
   ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
   ncclResult_t (*Reduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
   void load() {
@@ -516,6 +523,7 @@ struct NcclApi {
     GetVersion = reinterpret_cast<decltype(GetVersion)>(sym("ncclGetVersion"));
     CommInitAll = reinterpret_cast<decltype(CommInitAll)>(sym("ncclCommInitAll"));
     CommDestroy = reinterpret_cast<decltype(CommDestroy)>(sym("ncclCommDestroy"));
+    CommAbort = reinterpret_cast<decltype(CommAbort)>(sym("ncclCommAbort"));
     Reduce = reinterpret_cast<decltype(Reduce)>(sym("ncclReduce"));
     GetErrorString = reinterpret_cast<decltype(GetErrorString)>(sym("ncclGetErrorString"));
   }
@@ -530,7 +538,18 @@ struct ptc_multi {
   std::vector<ptc_scene *> scenes;
   std::vector<int> devices;
   std::vector<ncclComm_t> comms;  // empty for one device
+  bool comms_dead = false;        // a failed render aborted the communicators: the next call creates new ones
   NcclApi nccl;
+  void init_comms() {
+    comms.assign(devices.size(), nullptr);
+    nccl.check(nccl.CommInitAll(comms.data(), (int)devices.size(), devices.data()), "ncclCommInitAll");
+    comms_dead = false;
+  }
+  void abort_comms() {  // unblocks every rank that waits inside the collective
+    for (size_t i = 0; i < comms.size(); i++)
+      if (comms[i]) nccl.CommAbort(comms[i]), comms[i] = nullptr;
+    comms_dead = true;
+  }
   ~ptc_multi() {
     for (size_t i = 0; i < comms.size(); i++) {
       cudaSetDevice(devices[i]);
@@ -667,7 +686,9 @@ int ptc_render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_
                           void *cuda_stream, ptc_stats *stats) {
   PTC_GUARD_BEGIN
   require_committed(s);
-  render_accumulate(s, cam, st, d_accum, cuda_stream ? (cudaStream_t)cuda_stream : s->own_stream, stats);
+  // the caller's handle is honoured as given: NULL is the legacy default stream, which orders the film atomics after
+  // whatever the caller queued there (a memset of d_accum, a wait on a collective)
+  render_accumulate(s, cam, st, d_accum, (cudaStream_t)cuda_stream, stats);
   return 0;
   PTC_GUARD_END
 }
@@ -901,8 +922,7 @@ int ptc_multi_create(ptc_scene *primary, const int *devices, int n, ptc_multi **
   }
   if (n > 1) {
     m->nccl.load();
-    m->comms.assign((size_t)n, nullptr);
-    m->nccl.check(m->nccl.CommInitAll(m->comms.data(), n, devices), "ncclCommInitAll");
+    m->init_comms();
   }
   CK(cudaSetDevice(primary->device));
   *out = m.release();
@@ -927,12 +947,21 @@ static int multi_render(ptc_multi *m, const ptc_camera *cam, const ptc_render_se
   std::vector<ptc_stats> per((size_t)n);
   std::vector<std::string> errors((size_t)n);
   const auto t0 = std::chrono::steady_clock::now();
+  // Everything that can fail for lack of memory happens before the first thread starts: a worker that dropped out
+  // ahead of the collective would leave the other devices waiting in ncclReduce for ever.
+  if (n > 1 && m->comms_dead) m->init_comms();
+  for (int i = 0; i < n; i++) {
+    ptc_scene *s = m->scenes[(size_t)i];
+    CK(cudaSetDevice(s->device));
+    if (s->w_film.n < count) s->w_film.alloc(count);
+  }
+  std::mutex abort_mutex;
   auto work = [&](int i) {
+    ptc_scene *s = m->scenes[(size_t)i];
+    cudaStream_t stream = s->own_stream;
+    bool film_ok = false;
     try {
-      ptc_scene *s = m->scenes[(size_t)i];
       CK(cudaSetDevice(s->device));
-      if (s->w_film.n < count) s->w_film.alloc(count);
-      cudaStream_t stream = s->own_stream;
       CK(cudaMemsetAsync(s->w_film.p, 0, count * sizeof(float), stream));
       ptc_render_settings mine = *st;
       bool idle = false;
@@ -947,11 +976,25 @@ static int multi_render(ptc_multi *m, const ptc_camera *cam, const ptc_render_se
       }
       memset(&per[(size_t)i], 0, sizeof(ptc_stats));
       if (!idle) render_accumulate(s, cam, &mine, s->w_film.p, stream, &per[(size_t)i]);
-      // the single exchange step of the path: sum of the radiance films to devices[0]
-      if (n > 1) m->nccl.check(m->nccl.Reduce(s->w_film.p, s->w_film.p, count, ncclFloat, ncclSum, 0, m->comms[(size_t)i], stream), "ncclReduce");
-      CK(cudaStreamSynchronize(stream));
+      film_ok = true;
     } catch (std::exception &e) {
       errors[(size_t)i] = e.what();
+    }
+    if (n == 1) {
+      if (film_ok && cudaStreamSynchronize(stream) != cudaSuccess) errors[(size_t)i] = "cudaStreamSynchronize failed";
+      return;
+    }
+    // the single exchange step of the path: sum of the radiance films to devices[0].  A device whose render
+    // failed still takes part, with a zeroed film, so that the others return; if it cannot even do that the
+    // communicators are aborted (and re-created by the next call).
+    try {
+      if (!film_ok) CK(cudaMemsetAsync(s->w_film.p, 0, count * sizeof(float), stream));
+      m->nccl.check(m->nccl.Reduce(s->w_film.p, s->w_film.p, count, ncclFloat, ncclSum, 0, m->comms[(size_t)i], stream), "ncclReduce");
+      CK(cudaStreamSynchronize(stream));
+    } catch (std::exception &e) {
+      if (errors[(size_t)i].empty()) errors[(size_t)i] = e.what();
+      std::lock_guard<std::mutex> lock(abort_mutex);
+      if (!m->comms_dead) m->abort_comms();
     }
   };
   std::vector<std::thread> threads;

@@ -38,10 +38,10 @@ def render_sharded(render_fn, spp, mode="samples", group=None, dst=0):
     (W*H*3).  Returns the mean-radiance film (sum / spp) on rank `dst`, None elsewhere."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
-    b, e, tm, tr = shard(mode, spp, rank, world)
-    film = render_fn(b, e, tm, tr) if e > b else None
-    if film is None:
+    if mode == "samples" and world > spp:  # decided from (spp, world) alone, so every rank raises — none waits in the reduce
         raise ValueError("more ranks than samples: use mode='tiles'")
+    b, e, tm, tr = shard(mode, spp, rank, world)
+    film = render_fn(b, e, tm, tr)
     if world > 1:
         dist.reduce(film, dst=dst, op=dist.ReduceOp.SUM, group=group)  # the single exchange step of the path
     if rank != dst:

@@ -2,6 +2,7 @@
 // no oracle.  Each function cites the reference code whose behaviour it mirrors (paths under /root/reference).
 #include "../../include/pthost.h"
 
+#include <dlfcn.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -13,6 +14,7 @@
 #include <map>
 #include <sstream>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "json.hpp"
@@ -1133,54 +1135,112 @@ pth_scene *pth_scene_synthetic(int32_t cells, uint32_t seed) {
   return s.release();
 }
 
+// The product core is bound when first needed, not at link time: loading a scene description (tests of the loader, the
+// CPU reference arm of bench.py) must not map the CUDA library.  libptcore.so is looked up next to this library.
+namespace {
+struct CoreApi {
+  decltype(&::ptc_last_error) last_error = nullptr;
+  decltype(&::ptc_scene_create) scene_create = nullptr;
+  decltype(&::ptc_scene_destroy) scene_destroy = nullptr;
+  decltype(&::ptc_scene_add_material) add_material = nullptr;
+  decltype(&::ptc_scene_add_sphere) add_sphere = nullptr;
+  decltype(&::ptc_scene_add_plane) add_plane = nullptr;
+  decltype(&::ptc_scene_add_quad) add_quad = nullptr;
+  decltype(&::ptc_scene_add_cube) add_cube = nullptr;
+  decltype(&::ptc_scene_add_mesh) add_mesh = nullptr;
+  decltype(&::ptc_scene_set_sky_hdr) set_sky_hdr = nullptr;
+  decltype(&::ptc_scene_commit) commit = nullptr;
+  decltype(&::ptc_render_u32) render_u32 = nullptr;
+  bool ok = false;
+  std::string err;
+  CoreApi() {
+    void *lib = nullptr;
+    Dl_info info;
+    if (dladdr((void *)&pth_last_error, &info) && info.dli_fname) {
+      std::string dir(info.dli_fname);
+      const size_t k = dir.rfind('/');
+      dir = k == std::string::npos ? std::string(".") : dir.substr(0, k);
+      lib = dlopen((dir + "/libptcore.so").c_str(), RTLD_NOW | RTLD_GLOBAL);
+    }
+    if (!lib) lib = dlopen("libptcore.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) {
+      err = std::string("libptcore.so not found (the path tracer has no CPU fallback): ") + dlerror();
+      return;
+    }
+    bool all = true;
+    auto bind = [&](auto &fn, const char *name) {
+      fn = reinterpret_cast<std::remove_reference_t<decltype(fn)>>(dlsym(lib, name));
+      if (!fn) all = false, err = std::string("libptcore.so does not export ") + name;
+    };
+    bind(last_error, "ptc_last_error"), bind(scene_create, "ptc_scene_create"), bind(scene_destroy, "ptc_scene_destroy");
+    bind(add_material, "ptc_scene_add_material"), bind(add_sphere, "ptc_scene_add_sphere"), bind(add_plane, "ptc_scene_add_plane");
+    bind(add_quad, "ptc_scene_add_quad"), bind(add_cube, "ptc_scene_add_cube"), bind(add_mesh, "ptc_scene_add_mesh");
+    bind(set_sky_hdr, "ptc_scene_set_sky_hdr"), bind(commit, "ptc_scene_commit"), bind(render_u32, "ptc_render_u32");
+    ok = all;
+  }
+};
+const CoreApi *core_api() {
+  static const CoreApi api;
+  if (!api.ok) {
+    g_err = api.err;
+    return nullptr;
+  }
+  return &api;
+}
+}  // namespace
+
 ptc_scene *pth_build_ptc_scene(const pth_scene *s) {
-  ptc_scene *c = ptc_scene_create();
+  const CoreApi *api = core_api();
+  if (!api) return nullptr;
+  ptc_scene *c = api->scene_create();
   if (!c) {
-    g_err = ptc_last_error();
+    g_err = api->last_error();
     return nullptr;
   }
   auto fail = [&]() -> ptc_scene * {
-    g_err = ptc_last_error();
-    ptc_scene_destroy(c);
+    g_err = api->last_error();
+    api->scene_destroy(c);
     return nullptr;
   };
   for (const ptc_material &m : s->materials)
-    if (ptc_scene_add_material(c, &m) < 0) return fail();
+    if (api->add_material(c, &m) < 0) return fail();
   for (const pth_object &o : s->objects) {
     int r = 0;
     switch (o.type) {
-      case PTH_SPHERE: r = ptc_scene_add_sphere(c, o.center, o.radius, o.material); break;
-      case PTH_PLANE: r = ptc_scene_add_plane(c, o.p1, o.normal, o.material); break;
+      case PTH_SPHERE: r = api->add_sphere(c, o.center, o.radius, o.material); break;
+      case PTH_PLANE: r = api->add_plane(c, o.p1, o.normal, o.material); break;
       case PTH_QUAD:
-        r = ptc_scene_add_quad(c, o.base, o.edge0, o.edge1, o.normal, o.d, o.inv_edge0_len_sq, o.inv_edge1_len_sq, o.material);
+        r = api->add_quad(c, o.base, o.edge0, o.edge1, o.normal, o.d, o.inv_edge0_len_sq, o.inv_edge1_len_sq, o.material);
         break;
-      case PTH_CUBE: r = ptc_scene_add_cube(c, o.o2w, o.w2o, o.material); break;
+      case PTH_CUBE: r = api->add_cube(c, o.o2w, o.w2o, o.material); break;
       case PTH_MESH: {
         const std::vector<float> &t = s->meshes[(size_t)o.mesh];
-        r = ptc_scene_add_mesh(c, t.data(), (int64_t)(t.size() / 12), o.o2w, o.w2o, o.material);
+        r = api->add_mesh(c, t.data(), (int64_t)(t.size() / 12), o.o2w, o.w2o, o.material);
         break;
       }
       default: r = PTC_E_INVALID;
     }
     if (r < 0) return fail();
   }
-  if (!s->sky.empty() && ptc_scene_set_sky_hdr(c, s->sky.data(), s->sky_w, s->sky_h) < 0) return fail();
+  if (!s->sky.empty() && api->set_sky_hdr(c, s->sky.data(), s->sky_w, s->sky_h) < 0) return fail();
   return c;
 }
 
 // render_scene (renderer.rs:67-123): everything between the two lines of that function is the GPU core.
 int pth_render_scene(const pth_scene *s, int device, uint32_t *out_u32, ptc_stats *stats) {
+  const CoreApi *api = core_api();
+  if (!api) return PTC_E_INVALID;
   ptc_scene *c = pth_build_ptc_scene(s);
   if (!c) return PTC_E_INVALID;
-  int r = ptc_scene_commit(c, device);
+  int r = api->commit(c, device);
   if (r == 0) {
     ptc_render_settings st;
     memset(&st, 0, sizeof(st));
     st.width = s->width, st.height = s->height, st.spp = s->spp, st.max_depth = s->max_depth;
-    r = ptc_render_u32(c, &s->camera, &st, out_u32, stats);
+    r = api->render_u32(c, &s->camera, &st, out_u32, stats);
   }
-  if (r != 0) g_err = ptc_last_error();
-  ptc_scene_destroy(c);
+  if (r != 0) g_err = api->last_error();
+  api->scene_destroy(c);
   return r;
 }
 

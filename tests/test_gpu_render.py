@@ -27,16 +27,24 @@ def relmse(a, b):
 
 
 def _same_stream(pt, scene, w, h, spp, depth, seed=3):
+    """Image parity with the oracle on the SAME Philox streams, for both routes through the drain: the staged kernels to the
+    last ray (PTC_FLAG_NO_TAIL) and the default, where the last few thousand rays finish inside k_shade (stage_tail) —
+    at these sizes the default runs most of the render there, so the two renders cover the two code paths."""
     cs = scene.to_core().commit(0)
-    st = scene.render_settings(width=w, height=h, spp=spp, max_depth=depth, seed=seed)
-    img, stats = cs.render(scene.camera, st)
     ref, ostats = OracleScene(scene).render(scene.camera, w, h, spp, depth, rng_mode=RNG_PHILOX, seed=seed)
-    close = np.isclose(img, ref, rtol=1e-3, atol=1e-4).all(axis=2).mean()
-    assert close >= 0.995, close
-    assert stats.paths == w * h * spp == ostats.paths
-    assert abs(int(stats.rays) - int(ostats.rays)) <= 1e-3 * ostats.rays
-    assert abs(img.mean() - ref.mean()) <= 2e-3 * ref.mean()
-    return img, ref, stats
+    out = None
+    for flags in (pt.FLAG_NO_TAIL, 0):
+        st = scene.render_settings(width=w, height=h, spp=spp, max_depth=depth, seed=seed, flags=flags)
+        img, stats = cs.render(scene.camera, st)
+        close = np.isclose(img, ref, rtol=1e-3, atol=1e-4).all(axis=2).mean()
+        assert close >= 0.995, (flags, close)
+        assert stats.paths == w * h * spp == ostats.paths
+        assert abs(int(stats.rays) - int(ostats.rays)) <= 1e-3 * ostats.rays
+        assert abs(img.mean() - ref.mean()) <= 2e-3 * ref.mean()
+        if out is not None:  # the two routes run the same device functions on the same streams
+            assert stats.rays == out[2].rays and np.allclose(img, out[0], rtol=1e-5, atol=1e-6)
+        out = (img, ref, stats)
+    return out
 
 
 @pytest.mark.parametrize("name,w,h,spp,depth", [("cornell-box/scene.json", 128, 128, 16, 8),     # C1 shrunk
@@ -58,6 +66,55 @@ def test_shipped_teapot_scene_with_loader_extensions(pt):
     r = compare_hits(got, want)
     assert r["id_mismatch"] == 0 and r["t_mismatch"] == 0 and r["bit_exact_records"] == r["both_hit"] > 20000, r
     _same_stream(pt, s, 160, 90, 8, 12, seed=3)
+
+
+def test_config_c3_derived_same_stream(pt):
+    # BASELINE config C3 as derived in SURVEY.md 8d (teapot.obj x30, GGX copper, checker quad), shrunk frame
+    from raytracer_rust_b200 import workloads
+    _, s = workloads.workload("C3")
+    img, ref, stats = _same_stream(pt, s, 192, 108, 8, 16, seed=5)
+    assert stats.rays > 1.5 * stats.paths  # the copper teapot and the floor do scatter
+
+
+def test_config_c5_same_stream(pt):
+    # BASELINE config C5's generator (height field + glass sphere + GGX-Al cube + emissive quad), 300x300 cells =
+    # 180,000 triangles, shrunk frame, the config's own depth 16
+    s = pt.synthetic_scene(cells=300)
+    img, ref, stats = _same_stream(pt, s, 192, 108, 4, 16, seed=6)
+    assert stats.rays > 1.5 * stats.paths
+
+
+def test_tail_threshold_does_not_change_the_image(pt):
+    # a frame large enough that the staged kernels carry the bulk and the tail takes over late
+    s = pt.load_scene_from_json(os.path.join(SCENES, "semesterbild.json"))
+    cs = s.to_core().commit(0)
+    base = dict(width=400, height=300, spp=8, max_depth=30, seed=12)
+    a, sa = cs.render(s.camera, s.render_settings(flags=pt.FLAG_NO_TAIL, **base))
+    b, sb = cs.render(s.camera, s.render_settings(**base))
+    assert sa.rays == sb.rays and sa.paths == sb.paths == 400 * 300 * 8
+    assert sb.iterations < sa.iterations  # the tail cut the drain short
+    assert np.allclose(a, b, rtol=1e-5, atol=1e-6)
+
+
+def test_render_is_ordered_on_the_callers_stream(pt):
+    # ptc_render_accumulate with the NULL (legacy default) stream: work queued there beforehand — a long kernel, then the
+    # zeroing of the film — must be ordered before the render's film updates (the render used to run on a
+    # private non-blocking stream, so the memset could land in the middle of it)
+    torch = pytest.importorskip("torch")
+    s = pt.load_scene_from_json(os.path.join(SCENES, "cornell-box", "scene.json"))
+    cs = s.to_core().commit(0)
+    w = h = 96
+    st = s.render_settings(width=w, height=h, spp=4, max_depth=5, seed=8)
+    want, _ = cs.render(s.camera, st)
+    accum = torch.full((w * h * 3,), 1000.0, dtype=torch.float32, device="cuda:0")
+    for stream_ptr in (None, torch.cuda.current_stream().cuda_stream):
+        accum.fill_(1000.0)
+        torch.cuda.synchronize()
+        torch.cuda._sleep(400_000_000)  # ~0.2 s on the default stream
+        accum.zero_()
+        cs.render_accumulate(s.camera, st, accum.data_ptr(), stream_ptr)
+        got = accum.cpu().numpy().reshape(h, w, 3) / 4.0
+        assert np.allclose(got, want, rtol=1e-5, atol=1e-6), float(np.abs(got - want).max())
 
 
 def test_config_c1_full_size_same_stream(pt):

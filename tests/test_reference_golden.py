@@ -98,6 +98,6 @@ def _mesh_pos(scenes_dir):
 @pytest.mark.gpu
 def test_gpu_reproduces_the_references_own_render(pt, scenes_dir):
     s = pt.load_scene_from_json(os.path.join(scenes_dir, "semesterbild.json"))
-    buf, img, stats = pt.render_scene(s, 0, spp=64)
+    buf, img, stats = pt.render_scene(s, 0)  # the scene's native 800x600, 256 spp, depth 30 (config C2)
     d = _check(buf, mean_tol=0.8, frac10_tol=0.015, balance_tol=0.4)
-    assert stats.paths == 800 * 600 * 64
+    assert stats.paths == 800 * 600 * 256
