@@ -83,9 +83,7 @@ typedef struct ptc_render_settings {
 
 enum {
   PTC_FLAG_COUNTERS = 1, /* run the instrumented extend kernel: fills nodes_visited / tris_tested (slower) */
-  PTC_FLAG_TIMING = 2,   /* record CUDA events around every extend / shade launch: fills extend_ms / shade_ms */
-  PTC_FLAG_NO_TAIL = 4   /* keep the staged kernels to the last ray: never finish the drain's last few thousand rays inside
-                            the shade kernel (same image and ray count either way; for tests and measurements) */
+  PTC_FLAG_TIMING = 2    /* record CUDA events around every extend / shade launch: fills extend_ms / shade_ms */
 };
 
 /* HitRecord (src/hittable.rs:10-16) plus the ids the parity bar is stated on. */

@@ -477,8 +477,29 @@ struct BVHNode {  // bvh.rs:7-12
 };
 
 // bvh.rs:15-76.  `indices` is sorted in place, so after the build the index array is the DFS leaf order.
-// Rust's sort_unstable_by tie order depends on the std version: the oracle uses a STABLE sort (divergence class T6).
-std::unique_ptr<BVHNode> bvh_build(const std::vector<Triangle> &tris, size_t *idx, size_t n, size_t depth) {
+// Rust's sort_unstable_by tie order depends on the std version (pdqsort up to 1.80, ipnsort since; neither can be run or
+// pinned here): the oracle uses a STABLE sort by default (divergence class T6).  PTC_REF_TIE selects another order of
+// equal keys — `reverse` (reversed input order) or `random:<seed>` (hash of seed and triangle index) — so that the
+// sensitivity of the flat-node set to that unspecified order can be measured (tools/tie_order_study.py).
+struct TieOrder {
+  int kind = 0;  // 0 stable, 1 reverse, 2 random
+  uint64_t seed = 0;
+  static TieOrder from_env() {
+    TieOrder t;
+    const char *e = getenv("PTC_REF_TIE");
+    if (!e || !*e || !strcmp(e, "stable")) return t;
+    if (!strcmp(e, "reverse")) t.kind = 1;
+    else if (!strncmp(e, "random:", 7)) t.kind = 2, t.seed = strtoull(e + 7, nullptr, 10);
+    return t;
+  }
+  static uint64_t mix(uint64_t seed, uint64_t i) {  // splitmix64
+    uint64_t z = seed * 0x9E3779B97F4A7C15ull + i + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+  }
+};
+std::unique_ptr<BVHNode> bvh_build(const std::vector<Triangle> &tris, size_t *idx, size_t n, size_t depth, const TieOrder &tie = TieOrder()) {
   auto node = std::make_unique<BVHNode>();
   for (size_t i = 0; i < n; i++) {
     const Triangle &t = tris[idx[i]];
@@ -497,17 +518,29 @@ std::unique_ptr<BVHNode> bvh_build(const std::vector<Triangle> &tris, size_t *id
     const Triangle &t = tris[i];
     return ((t.v0 + t.v1 + t.v2) * (1.0f / 3.0f))[axis];
   };
-  std::stable_sort(idx, idx + n, [&](size_t a, size_t b) {
-    float va = centroid(a), vb = centroid(b);
-    return va < vb;  // partial_cmp(..).unwrap_or(Equal): NaN compares equal
-  });
+  if (tie.kind == 0) {
+    std::stable_sort(idx, idx + n, [&](size_t a, size_t b) {
+      float va = centroid(a), vb = centroid(b);
+      return va < vb;  // partial_cmp(..).unwrap_or(Equal): NaN compares equal
+    });
+  } else {
+    std::vector<std::pair<uint64_t, size_t>> sec(n);  // (secondary key realising the tie order, triangle)
+    for (size_t i = 0; i < n; i++) sec[i] = {tie.kind == 1 ? (uint64_t)(n - 1 - i) : TieOrder::mix(tie.seed, (uint64_t)idx[i]), idx[i]};
+    std::stable_sort(sec.begin(), sec.end(), [&](const std::pair<uint64_t, size_t> &a, const std::pair<uint64_t, size_t> &b) {
+      float va = centroid(a.second), vb = centroid(b.second);
+      if (va < vb) return true;
+      if (vb < va) return false;
+      return a.first < b.first;
+    });
+    for (size_t i = 0; i < n; i++) idx[i] = sec[i].second;
+  }
   size_t mid = n / 2;
   if (mid == 0 || mid == n) {
     node->triangle_indices.assign(idx, idx + n);
     return node;
   }
-  node->left = bvh_build(tris, idx, mid, depth + 1);
-  node->right = bvh_build(tris, idx + mid, n - mid, depth + 1);
+  node->left = bvh_build(tris, idx, mid, depth + 1, tie);
+  node->right = bvh_build(tris, idx + mid, n - mid, depth + 1, tie);
   return node;
 }
 
@@ -982,7 +1015,7 @@ int orc_scene_add_mesh(orc_scene *s, const float *tris, int64_t n, const float o
   }
   o->order.resize((size_t)n);
   for (size_t i = 0; i < (size_t)n; i++) o->order[i] = i;
-  o->bvh = bvh_build(o->triangles, o->order.data(), (size_t)n, 0);  // mesh_object.rs:44-45
+  o->bvh = bvh_build(o->triangles, o->order.data(), (size_t)n, 0, TieOrder::from_env());  // mesh_object.rs:44-45
   o->o2w = mat_from(o2w);
   o->w2o = mat_from(w2o);
   o->material = material;

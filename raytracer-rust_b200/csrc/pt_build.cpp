@@ -7,6 +7,9 @@
 #include <cmath>
 #include <cstring>
 #include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
 #include <chrono>
 #include <thread>
 
@@ -27,6 +30,8 @@ struct RefCtx {
   uint8_t *dead;
   std::atomic<int64_t> nodes{0}, leaves{0};
   std::atomic<int32_t> max_depth{0};
+  int tie_kind = 0;
+  uint64_t tie_seed = 0;
 };
 
 // The reference sorts a node's triangles with `sort_unstable_by` on one centroid coordinate (bvh.rs:45-53); the
@@ -41,8 +46,47 @@ inline uint32_t float_sort_key(float f) {
   memcpy(&u, &f, 4);
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
-void sort_by_centroid(int64_t *idx, int64_t n, const float *cen, int axis, uint64_t *scratch) {
+// Tie order of equal centroid keys (PTC_REF_TIE, read per build): what Rust's sort_unstable_by does with them is
+// unspecified and changes with the std version (pdqsort up to 1.80, ipnsort since), and it decides which triangles end up
+// together under a flat node.  The switch exists to MEASURE that sensitivity (tools/tie_order_study.py):
+//   stable (default)  equal keys keep their input order
+//   reverse           equal keys in reversed input order
+//   random:<seed>     equal keys ordered by a hash of (seed, triangle index)
+// The oracle (oracle/oracle.cpp: bvh_build) has the same switch; GPU-vs-oracle parity is tested under each.
+struct TieMode {
+  int kind = 0;  // 0 stable, 1 reverse, 2 random
+  uint64_t seed = 0;
+};
+TieMode tie_mode_from_env() {
+  TieMode t;
+  const char *e = getenv("PTC_REF_TIE");
+  if (!e || !*e || !strcmp(e, "stable")) return t;
+  if (!strcmp(e, "reverse")) t.kind = 1;
+  else if (!strncmp(e, "random:", 7)) t.kind = 2, t.seed = strtoull(e + 7, nullptr, 10);
+  else throw std::invalid_argument(std::string("PTC_REF_TIE: unknown tie order '") + e + "' (stable | reverse | random:<seed>)");
+  return t;
+}
+inline uint64_t tie_hash(uint64_t seed, uint64_t i) {  // splitmix64
+  uint64_t z = seed * 0x9E3779B97F4A7C15ull + i + 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+void sort_by_centroid(int64_t *idx, int64_t n, const float *cen, int axis, uint64_t *scratch, const TieMode &tie) {
   static const bool force_std = getenv("PTC_REF_STABLE_SORT") != nullptr;
+  if (tie.kind != 0) {
+    // secondary key that realises the tie order, then one stable sort on (key, secondary)
+    std::vector<std::pair<uint64_t, int64_t>> sec((size_t)n);
+    for (int64_t i = 0; i < n; i++) sec[(size_t)i] = {tie.kind == 1 ? (uint64_t)(n - 1 - i) : tie_hash(tie.seed, (uint64_t)idx[i]), idx[i]};
+    std::stable_sort(sec.begin(), sec.end(), [cen, axis](const std::pair<uint64_t, int64_t> &a, const std::pair<uint64_t, int64_t> &b) {
+      const float ka = cen[a.second * 3 + axis], kb = cen[b.second * 3 + axis];
+      if (ka < kb) return true;
+      if (kb < ka) return false;
+      return a.first < b.first;
+    });
+    for (int64_t i = 0; i < n; i++) idx[i] = sec[(size_t)i].second;
+    return;
+  }
   if (n < 4096 || force_std || scratch == nullptr) {
     std::stable_sort(idx, idx + n, [cen, axis](int64_t a, int64_t b) { return cen[a * 3 + axis] < cen[b * 3 + axis]; });
     return;
@@ -87,7 +131,9 @@ void ref_build(RefCtx &c, int64_t *idx, int64_t n, int depth, bool dead_in, int 
   }
   const float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
   const int axis = (ex > ey && ex > ez) ? 0 : (ey > ez ? 1 : 2);
-  sort_by_centroid(idx, n, c.cen, axis, scratch);
+  TieMode tie;
+  tie.kind = c.tie_kind, tie.seed = c.tie_seed;
+  sort_by_centroid(idx, n, c.cen, axis, scratch, tie);
   const int64_t mid = n / 2;
   uint64_t *s_left = scratch, *s_right = scratch ? scratch + 2 * mid : nullptr;
   if (par_levels > 0 && n > (1 << 14)) {
@@ -547,6 +593,8 @@ void build_mesh(MeshBuild &m, int threads) {
     rc.m = &m;
     rc.cen = cen.data();
     rc.dead = m.dead.data();
+    const TieMode tm = tie_mode_from_env();
+    rc.tie_kind = tm.kind, rc.tie_seed = tm.seed;
     std::vector<uint64_t> scratch(n >= 4096 ? (size_t)n * 2 : 0);
     ref_build(rc, idx.data(), n, 0, false, par_levels, scratch.empty() ? nullptr : scratch.data());
     m.ref_nodes = rc.nodes.load();
@@ -558,11 +606,12 @@ void build_mesh(MeshBuild &m, int threads) {
   const double ms_ref = ms_since(t_begin);
   auto t_sah = now();
 
-  // ---- normals by original index
+  // ---- normals by position in the reference's DFS leaf order (the traversal's result key carries that position), the
+  // original triangle index in .w
   m.normals.resize((size_t)n);
   for (int64_t i = 0; i < n; i++) {
     const float *t = tri_ptr(m, i);
-    m.normals[(size_t)i] = make_float4(t[9], t[10], t[11], 0.0f);
+    m.normals[(size_t)m.order[(size_t)i]] = make_float4(t[9], t[10], t[11], u2f_host((uint32_t)i));
   }
 
   // ---- step 2

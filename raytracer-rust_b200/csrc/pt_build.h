@@ -29,7 +29,7 @@ struct MeshBuild {
   // steps 2-3
   std::vector<Node8> nodes;
   std::vector<Tri48> tri48;
-  std::vector<float4> normals;  // n
+  std::vector<float4> normals;  // n: Triangle.normal by DFS position (`order`), original index bit-cast in .w
   int32_t wide_depth = 0;
   float root_lo[3] = {1, 1, 1}, root_hi[3] = {-1, -1, -1};  // padded root frame (inverted = nothing to hit)
   bool built = false;

@@ -181,7 +181,7 @@ PT_HD bool mesh_root_may_hit(const DMesh &mesh, const MeshRay &r, float t_min, f
 
 // Second half of Mesh::hit (mesh_object.rs:293-326): object-space closest triangle -> world-space HitRecord, with the
 // closed-interval recheck on the (quirky) world t.
-// `nq` = mesh.normals[mh.tri], loaded by the caller (k_extend_post issues it together with its other gathers).
+// `nq` = mesh.normals[mh.order], loaded by the caller (k_extend_post issues it together with its other gathers).
 PT_HD bool mesh_finish(const float *f, float4 nq, const Ray &ray, const MeshRay &mr, const MeshHit &mh, float t_min, float t_max,
                        Hit &h) {
   const M4 w2o = load_m4(f), o2w = load_m4(f + 16);
@@ -202,7 +202,7 @@ PT_HD bool mesh_finish(const float *f, float4 nq, const Ray &ray, const MeshRay 
 
 PT_HD bool mesh_finish(const float *f, const DMesh &mesh, const Ray &ray, const MeshRay &mr, const MeshHit &mh, float t_min,
                        float t_max, Hit &h) {
-  return mesh_finish(f, ldg4(mesh.normals + mh.tri), ray, mr, mh, t_min, t_max, h);
+  return mesh_finish(f, ldg4(mesh.normals + mh.order), ray, mr, mh, t_min, t_max, h);
 }
 
 // src/mesh/mesh_object.rs:262-329, straight line (parity hooks and the hostsim harness; the renderer splits it into

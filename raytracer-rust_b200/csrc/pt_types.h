@@ -65,7 +65,7 @@ struct alignas(16) Tri48 {
 struct DMesh {
   const float4 *nodes;    // Node8 array, root = node 0
   const float4 *tris;     // Tri48 array in leaf order
-  const float4 *normals;  // Triangle.normal by original index (.w unused)
+  const float4 *normals;  // Triangle.normal by position in the reference's DFS leaf order, original index bit-cast in .w
   int32_t n_nodes, n_tris;
   float root_lo[3], root_hi[3];  // padded frame of the root node: a ray that misses it cannot hit any live triangle
 };

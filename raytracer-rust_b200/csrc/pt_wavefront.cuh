@@ -36,8 +36,9 @@ using namespace pt;
 
 constexpr int kBlock = 256;    // threads per block of every stage kernel
 constexpr int kSegPerSM = 4;   // segments (= resident blocks) per SM: 4 x 256 threads x <= 64 registers
-constexpr uint32_t kTailRays = 1u << 16;  // default of RenderParams::tail_rays
-constexpr uint32_t kRefillLanes = 8;  // a traversal warp fetches new tasks once this many lanes are idle
+constexpr uint32_t kRefillLanes = 8;
+constexpr uint32_t kNoSteal = 0x80000000u;  // bit of k_traverse's `refill_lanes` argument: in-warp work stealing off (measurements)
+constexpr unsigned long long kNoTriHit = ~0ull;  // a traversal warp fetches new tasks once this many lanes are idle
 
 // Device-side control block of one render
 struct Ctl {
@@ -45,10 +46,8 @@ struct Ctl {
   unsigned long long total_paths;  // path index space of this call (padded tiles x samples)
   unsigned long long rays;         // extend items so far = trace_ray calls with depth > 0
   unsigned long long nodes, tris, mesh_rays;  // PTC_FLAG_COUNTERS
-  uint32_t n_live[2];      // rays alive after the last shade (sum of the segment counts), per half-wavefront
-  uint32_t iterations[2];  // per half-wavefront
-  uint32_t prev_live;      // rays that entered the iteration in flight (written by k_extend_pre, read by k_shade's tail rule)
-  uint32_t tail_blocks;    // blocks that finished their segment inside k_shade (statistics)
+  uint32_t n_live[2];      // rays alive after the last shade (sum of the segment counts); [0] is used
+  uint32_t iterations[2];  // [0] is used
 };
 
 // A kernel launch covers segments [seg0, seg0 + gridDim.x).
@@ -65,8 +64,6 @@ struct RenderParams {
   int32_t sample_begin, n_samples;
   int32_t tiles_x, n_my_tiles, tile_mod, tile_rem;
   uint32_t row_mult;  // odd, coprime with n_my_tiles: scatters consecutive 32-pixel rows over the image (see k_shade)
-  uint32_t tail_rays;  // once the path supply is exhausted and at most this many rays are in flight, every block finishes its
-                       // own segment inside k_shade (stage_tail); 0 = never
   uint64_t seed;
 };
 
@@ -93,7 +90,8 @@ struct TaskQ {
   uint2 *ray[2];   // x = ray slot, y = object index of the mesh
   float4 *o[2];    // object-space origin, closest_so_far (the t_max Mesh::hit was called with)
   float4 *d[2];    // object-space direction (normalised twice, mesh_object.rs:287 + ray.rs:15)
-  float2 *res[2];  // traversal result: t (object space), original triangle index or 0xffffffff
+  unsigned long long *res[2];  // traversal result: f2u(t) << 32 | reference DFS position of the triangle (kNoTriHit = none); set to
+                               // kNoTriHit when the ray is parked, lowered with atomicMin by every lane that worked on the task
   uint32_t *cnt;   // [(rounds + 1) * S]
 };
 
@@ -177,6 +175,7 @@ __device__ __forceinline__ void park_tasks(uint32_t *s_ntask, const TaskQ &tq, i
     tq.ray[par][slot] = make_uint2(i, (uint32_t)park);
     tq.o[par][slot] = make_float4(mr.o.x, mr.o.y, mr.o.z, closest);
     tq.d[par][slot] = make_float4(mr.d.x, mr.d.y, mr.d.z, 0.0f);
+    tq.res[par][slot] = kNoTriHit;
   }
 }
 
@@ -214,14 +213,26 @@ __device__ __forceinline__ void stage_pre(uint32_t seg, uint32_t n_seg, const DS
   (void)n_seg;
 }
 
+// Persistent warps over the block's tasks; every lane walks its own BVH one step at a time and idle lanes refetch from
+// the block's cursor.  Once the cursor is exhausted, idle lanes STEAL from busy ones of their warp: a donor hands over the
+// bottom entry of its stack (the farthest pending node group) or, with an empty stack, the lowest-priority child of the
+// group it is working on; the thief copies the donor's ray by shuffles and walks that subtree for the same task.  Every
+// lane that finds a hit lowers the task's 64-bit result key (t, DFS position) with one atomicMin, so the result is the
+// same closest hit whatever the split.  Why: a launch ends when its LAST traversal ends, and in the drain of a render
+// (a few deep paths inside the glass sphere) a launch IS one or two 40-step traversals: 36-42 us per launch at ~0.8 us
+// per dependent node step (profiles/r1_v4_launches.csv), the largest part of the per-iteration floor that limits strong
+// scaling.  Split over the idle lanes the same walk is a few steps deep.
 template <bool COUNT>
 __device__ __forceinline__ void stage_traverse(uint32_t seg, uint32_t n_seg, Ctl *ctl, const DScene &sc, const TaskQ &tq, int round,
-                                               float t_min, uint32_t cap, uint32_t refill_lanes) {
+                                               float t_min, uint32_t cap, uint32_t refill_arg) {
   __shared__ uint32_t s_cur;
   const uint32_t n = tq.cnt[(uint32_t)round * n_seg + seg], seg_base = seg * cap;
   const int par = round & 1;
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t lt_mask = (1u << lane) - 1u;
+  const uint32_t refill_lanes = refill_arg & ~kNoSteal;
+  const bool steal = (refill_arg & kNoSteal) == 0u;
+  const uint32_t quota = (n >= (uint32_t)kBlock || !steal) ? 32u : max(1u, (n + (uint32_t)(kBlock / 32) - 1u) / (uint32_t)(kBlock / 32));
   if (threadIdx.x == 0) s_cur = 0;
   __syncthreads();
   TraversalCounters tc{0u, 0u, 0u};
@@ -229,19 +240,23 @@ __device__ __forceinline__ void stage_traverse(uint32_t seg, uint32_t n_seg, Ctl
   DMesh mesh;  // the two pointers of the mesh this lane walks, kept in registers
   mesh.nodes = nullptr, mesh.tris = nullptr;
   uint2 stack[kTraversalStack];
-  int sp = 0;
+  int sp = 0, sb = 0;  // live entries: [sb, sp)
   bool active = false;
   uint32_t task = 0;
   bool exhausted = n == 0u;
+  s.ng = make_uint2(0u, 0u);
   for (;;) {
     const uint32_t idle = __ballot_sync(0xffffffffu, !active);
     if (!exhausted && (idle == 0xffffffffu || (uint32_t)__popc(idle) >= refill_lanes)) {
-      const uint32_t cnt = (uint32_t)__popc(idle);
+      // a block with few tasks (the drain of a render: a few dozen per segment) spreads them over all its warps instead
+      // of filling the first two: the idle lanes next to every walker are what the stealing below splits long walks over
+      const uint32_t cnt = min((uint32_t)__popc(idle), quota);
       uint32_t base = 0;
       if (lane == 0) base = atomicAdd(&s_cur, cnt);  // shared memory: the block's own cursor
       base = __shfl_sync(0xffffffffu, base, 0);
-      if (!active) {
-        const uint32_t j = base + (uint32_t)__popc(idle & lt_mask);
+      const uint32_t my_rank = (uint32_t)__popc(idle & lt_mask);
+      if (!active && my_rank < cnt) {
+        const uint32_t j = base + my_rank;
         if (j < n) {
           const uint32_t slot = seg_base + j;
           const uint2 rk = tq.ray[par][slot];
@@ -250,13 +265,55 @@ __device__ __forceinline__ void stage_traverse(uint32_t seg, uint32_t n_seg, Ctl
           mesh.nodes = gm->nodes;
           mesh.tris = gm->tris;
           trav_begin(s, v3(o4.x, o4.y, o4.z), v3(d4.x, d4.y, d4.z), t_min, o4.w);  // world t bounds, mesh_object.rs:289-291
-          sp = 0;
+          sp = sb = 0;
           task = slot;
           active = true;
           if (COUNT) tc.mesh_rays++;
         }
       }
       if (base + cnt >= n) exhausted = true;
+    } else if (steal && exhausted && idle != 0u && idle != 0xffffffffu) {
+      const bool can_give = active && (sp > sb || __popc(s.ng.y >> 24) >= 2);
+      const uint32_t donors = __ballot_sync(0xffffffffu, can_give);
+      if (donors != 0u) {
+        const uint32_t pairs = (uint32_t)min(__popc(idle), __popc(donors));
+        const bool give = can_give && (uint32_t)__popc(donors & lt_mask) < pairs;
+        const uint32_t my_idle_rank = (uint32_t)__popc(idle & lt_mask);
+        const bool take = !active && my_idle_rank < pairs;
+        uint2 entry = make_uint2(0u, 0u);
+        if (give) {
+          if (sp > sb) {
+            entry = stack[sb++];
+          } else {  // split the group in hand: its lowest-priority pending child goes
+            const uint32_t pend = s.ng.y & 0xFF000000u, bit = pend & (0u - pend);
+            entry = make_uint2(s.ng.x, bit | (s.ng.y & 0xffu));
+            s.ng.y &= ~bit;
+          }
+        }
+        const int src = take ? (int)__fns(donors, 0u, (int)my_idle_rank + 1) : (int)lane;
+        const float ox = __shfl_sync(0xffffffffu, s.o.x, src), oy = __shfl_sync(0xffffffffu, s.o.y, src), oz = __shfl_sync(0xffffffffu, s.o.z, src);
+        const float dx = __shfl_sync(0xffffffffu, s.d.x, src), dy = __shfl_sync(0xffffffffu, s.d.y, src), dz = __shfl_sync(0xffffffffu, s.d.z, src);
+        const float ix = __shfl_sync(0xffffffffu, s.idx, src), iy = __shfl_sync(0xffffffffu, s.idy, src), iz = __shfl_sync(0xffffffffu, s.idz, src);
+        const float tmn = __shfl_sync(0xffffffffu, s.t_min, src), bt = __shfl_sync(0xffffffffu, s.best_t, src);
+        const uint32_t bo = __shfl_sync(0xffffffffu, s.best_order, src), oi = __shfl_sync(0xffffffffu, s.octinv, src);
+        const uint32_t ex = __shfl_sync(0xffffffffu, entry.x, src), ey = __shfl_sync(0xffffffffu, entry.y, src);
+        const uint32_t tk = __shfl_sync(0xffffffffu, task, src);
+        const unsigned long long pn = __shfl_sync(0xffffffffu, (unsigned long long)mesh.nodes, src);
+        const unsigned long long ptri = __shfl_sync(0xffffffffu, (unsigned long long)mesh.tris, src);
+        if (take) {
+          s.o = v3(ox, oy, oz), s.d = v3(dx, dy, dz);
+          s.idx = ix, s.idy = iy, s.idz = iz;
+          s.t_min = tmn, s.best_t = bt, s.best_order = bo, s.octinv = oi;
+          s.best_tri = 0xffffffffu;  // "nothing found by THIS lane": the donor's best only prunes
+          s.ng = make_uint2(ex, ey);
+          s.tg = make_uint2(0u, 0u), s.tg2 = make_uint2(0u, 0u);
+          mesh.nodes = reinterpret_cast<const float4 *>(pn);
+          mesh.tris = reinterpret_cast<const float4 *>(ptri);
+          task = tk;
+          sp = sb = 0;
+          active = true;
+        }
+      }
     }
     if (__ballot_sync(0xffffffffu, active) == 0u) {
       if (exhausted) break;
@@ -265,12 +322,14 @@ __device__ __forceinline__ void stage_traverse(uint32_t seg, uint32_t n_seg, Ctl
     if (active) {
       // one node step AND one triangle test per turn: the node step does not wait for the lane's pending triangles
       if (!trav_has_node(s)) {
-        if (sp > 0) {
+        if (sp > sb) {
           s.ng = stack[--sp];
         } else if (!trav_has_tri(s)) {
-          tq.res[par][task] = make_float2(s.best_t, u2f(s.best_tri));
+          if (s.best_tri != 0xffffffffu) atomicMin(&tq.res[par][task], ((unsigned long long)f2u(s.best_t) << 32) | (unsigned long long)s.best_order);
           active = false;
+          s.ng.y = 0u;
         }
+        if (sp == sb) sp = sb = 0;
       }
       if (active && trav_has_node(s) && s.tg2.y == 0u) trav_node<COUNT>(mesh, s, stack, sp, &tc);
       if (active && trav_has_tri(s)) trav_tri<COUNT>(mesh, s, &tc);
@@ -303,26 +362,27 @@ __device__ __forceinline__ void stage_post(uint32_t seg, uint32_t n_seg, const D
     uint32_t i = 0;
     if (c0 + tid < n) {
       const uint2 rk = tq.ray[par][j];
-      const float2 res = tq.res[par][j];
+      const unsigned long long res = tq.res[par][j];
       i = rk.x;
       const int k = (int)rk.y;
       const DObject *ob = objs + k;
-      const uint32_t tri = f2u(res.y);
+      const bool tri_hit = res != kNoTriHit;
+      const uint32_t order = (uint32_t)res;
       // the stage is bound by the latency of these gathers: issue all of them before the first use
       const float4 o4 = out.b.ray_o[i], d4 = out.b.ray_d[i];
       const float h1w = out.b.hit1[i].w, h0w = out.b.hit0[i].w;
       float4 nq = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-      if (tri != 0xffffffffu) nq = ldg4(sc.meshes[ob->mesh].normals + tri);
+      if (tri_hit) nq = ldg4(sc.meshes[ob->mesh].normals + order);  // normal + original index, by DFS position
       const Ray ray{v3(o4.x, o4.y, o4.z), v3(d4.x, d4.y, d4.z)};
       const bool any = (f2u(h1w) & kHitBit) != 0u;
       if (any) closest = h0w;  // == the t_max the traversal ran with
       Hit best;
       best.triangle = -1;
       bool improved = false;
-      if (tri != 0xffffffffu) {
+      if (tri_hit) {
         const MeshRay omr = mesh_object_ray<false>(ob->f, ray);  // same inputs, same bits as in k_extend_pre
         MeshHit mh;
-        mh.t = res.x, mh.tri = tri, mh.order = 0u;
+        mh.t = u2f((uint32_t)(res >> 32)), mh.tri = f2u(nq.w), mh.order = order;
         Hit tmp;
         if (mesh_finish(ob->f, nq, ray, omr, mh, t_min, closest, tmp)) {
           improved = true;
@@ -340,62 +400,6 @@ __device__ __forceinline__ void stage_post(uint32_t seg, uint32_t n_seg, const D
   }
   __syncthreads();
   if (tid == 0) tq.cnt[(uint32_t)(round + 1) * n_seg + seg] = s_ntask;
-}
-
-// ---- the drain's tail ---------------------------------------------------------------------------------------------
-// Once the path supply is exhausted every iteration carries fewer rays than the one before, and the last ~25 of a
-// depth-30 render carry a few thousand: four dependent launches of 592 blocks each, ~65 us per iteration, for work that
-// would fit a handful of warps — 2 ms of a C2 frame, and the part that does not shrink when the frame is split over
-// eight GPUs.  When at most `tail_rays` rays entered the iteration in flight, every block therefore finishes the
-// survivors of ITS segment right here: one thread per ray runs trace_ray's loop (renderer.rs:19-65) to the end with the
-// straight-line closest hit (scene_hit: the same device functions, the same bits as the staged kernels) and the same
-// Philox keys (pixel, sample, bounce), so the image and the ray count are those of the staged iterations.  The cost is
-// the longest remaining path's dependent chain (~10 us per bounce) instead of one iteration per bounce.
-__device__ __noinline__ void stage_tail(uint32_t seg_base, uint32_t n, Ctl *ctl, const DScene &sc, const RenderParams &rp, const Buffers &b,
-                                        float *accum) {
-  unsigned long long my_rays = 0;
-  for (uint32_t j = threadIdx.x; j < n; j += (uint32_t)kBlock) {
-    const float4 o4 = b.nray_o[seg_base + j], d4 = b.nray_d[seg_base + j], b4 = b.nbeta[seg_base + j];
-    const uint32_t pixel = f2u(o4.w), sample = f2u(d4.w);
-    uint32_t bounce = f2u(b4.w);
-    Ray ray{v3(o4.x, o4.y, o4.z), v3(d4.x, d4.y, d4.z)};
-    V3 beta = v3(b4.x, b4.y, b4.z);
-    V3 radiance = v3(0, 0, 0);
-    bool add = false;
-    for (;;) {
-      my_rays++;
-      Hit best;
-      if (!scene_hit<false>(sc, ray, kEps, INFINITY, best, nullptr)) {  // renderer.rs:24, 38-63
-        radiance = radiance + beta * sky_color(sc, ray.d);
-        add = true;
-        break;
-      }
-      const DMaterial m = sc.materials[best.material];
-      const V3 e = mat_emitted(m);
-      if (e.x != 0.0f || e.y != 0.0f || e.z != 0.0f) {
-        radiance = radiance + beta * e;
-        add = true;
-      }
-      const Uniforms4 u = philox_uniforms(rp.seed, pixel, sample, bounce, 0u);
-      Ray sc_ray;
-      V3 att;
-      if (!mat_scatter(m, ray.d, v3(best.px, best.py, best.pz), v3(best.nx, best.ny, best.nz), best.front_face != 0, u.u, sc_ray, att)) break;
-      if (bounce + 1u >= (uint32_t)rp.max_depth) break;  // trace_ray(scattered, 0) is black (renderer.rs:20-22)
-      beta = beta * att;
-      ray = sc_ray;
-      bounce++;
-    }
-    if (add) {
-      float *px = accum + (size_t)pixel * 3;
-      atomicAdd(px + 0, radiance.x);
-      atomicAdd(px + 1, radiance.y);
-      atomicAdd(px + 2, radiance.z);
-    }
-  }
-  // one global atomic per warp (a block has at most a few hundred rays here)
-  for (int d = 16; d > 0; d >>= 1) my_rays += __shfl_xor_sync(0xffffffffu, my_rays, d);
-  if ((threadIdx.x & 31u) == 0u && my_rays) atomicAdd(&ctl->rays, my_rays);
-  if (threadIdx.x == 0) atomicAdd(&ctl->tail_blocks, 1u);
 }
 
 constexpr int kShadeClasses = 10;  // 0 = miss, 1 + material type (8 types), 9 = no ray (tail of the last window)
@@ -630,19 +634,6 @@ __device__ __forceinline__ uint32_t stage_shade(uint32_t seg, uint32_t n_seg, ui
     __syncthreads();
     if (!again) break;
   }
-  // the tail rule (see stage_tail), decided by one thread so that the whole block agrees: prev_live was written by the
-  // k_extend_pre of this iteration, next_path only grows
-  if (rp.tail_rays != 0u) {
-    if (tid == 0) {
-      const uint32_t in_flight = ctl->prev_live;
-      s_more = (w != 0u && in_flight != 0u && in_flight <= rp.tail_rays && ctl->next_path >= ctl->total_paths) ? 1u : 0u;
-    }
-    __syncthreads();
-    if (s_more != 0u) {
-      stage_tail(seg_base, w, ctl, sc, rp, b, accum);
-      w = 0u;
-    }
-  }
   if (tid == 0) {
     b.cnt[seg] = w;
     if (w) atomicAdd(&ctl->n_live[half], w);
@@ -671,7 +662,6 @@ __global__ void __launch_bounds__(kBlock, kSegPerSM) k_extend_pre(Ctl *ctl, SegR
       atomicAdd(&ctl->rays, (unsigned long long)live);
       ctl->iterations[sr.half]++;
     }
-    ctl->prev_live = live;
     ctl->n_live[sr.half] = 0;
   }
   if (sc.n_objects <= kSmemObjects) stage_pre<true>(sr.seg0 + blockIdx.x, sr.n_seg, sc, out, tq, t_min, t_max);
@@ -693,7 +683,6 @@ __global__ void __launch_bounds__(kBlock, kSegPerSM) k_shade(Ctl *ctl, SegRange 
   pdl_prologue();
   stage_shade(sr.seg0 + blockIdx.x, sr.n_seg, sr.half, ctl, sc, rp, b, accum);
 }
-
 
 // out = rgb * scale (renderer.rs:103)
 __global__ void k_scale(const float *in, float *out, size_t n, float scale) {

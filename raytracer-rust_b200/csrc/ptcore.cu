@@ -80,7 +80,7 @@ struct Workspace {
   DevBuf<uint32_t> cnt;
   DevBuf<uint2> tq_ray[2];
   DevBuf<float4> tq_o[2], tq_d[2];
-  DevBuf<float2> tq_res[2];
+  DevBuf<unsigned long long> tq_res[2];
   DevBuf<uint32_t> tq_cnt;
   DevBuf<int2> ids;
 
@@ -176,6 +176,13 @@ void launch_stage(bool pdl, cudaStream_t stream, uint32_t segments, void (*kerne
   CK(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
 }
 
+// k_traverse's `refill_lanes` argument.  PTC_REFILL: idle lanes that trigger a task fetch; PTC_STEAL=0: in-warp work
+// stealing off (both read per call, for A/B measurements and tests)
+uint32_t traverse_refill_arg() {
+  const char *r = getenv("PTC_REFILL"), *st = getenv("PTC_STEAL");
+  return (r ? (uint32_t)atoi(r) : kRefillLanes) | ((st && atoi(st) == 0) ? kNoSteal : 0u);
+}
+
 // One extend pass over ALL segments on one stream (ptc_intersect) = pre, then (traverse, post) once per mesh object a ray
 // can meet.  Returns the number of launches.
 int launch_extend(cudaStream_t stream, uint32_t segments, int rounds, Ctl *ctl, const DScene &ds, const ExtendOut &eo, const TaskQ &tq,
@@ -183,8 +190,8 @@ int launch_extend(cudaStream_t stream, uint32_t segments, int rounds, Ctl *ctl, 
   const SegRange sr{0u, segments, 0u};
   k_extend_pre<<<segments, kBlock, 0, stream>>>(ctl, sr, ds, eo, tq, t_min, t_max);
   for (int r = 0; r < rounds; r++) {
-    if (counters) k_traverse<true><<<segments, kBlock, 0, stream>>>(ctl, sr, ds, tq, r, t_min, eo.b.cap, kRefillLanes);
-    else k_traverse<false><<<segments, kBlock, 0, stream>>>(ctl, sr, ds, tq, r, t_min, eo.b.cap, kRefillLanes);
+    if (counters) k_traverse<true><<<segments, kBlock, 0, stream>>>(ctl, sr, ds, tq, r, t_min, eo.b.cap, traverse_refill_arg());
+    else k_traverse<false><<<segments, kBlock, 0, stream>>>(ctl, sr, ds, tq, r, t_min, eo.b.cap, traverse_refill_arg());
     k_extend_post<<<segments, kBlock, 0, stream>>>(sr, ds, eo, tq, r, t_min, t_max);
   }
   return 1 + 2 * rounds;
@@ -245,11 +252,6 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
   rp.n_my_tiles = tile_rem < n_tiles ? (n_tiles - tile_rem + tile_mod - 1) / tile_mod : 0;
   rp.tile_mod = tile_mod, rp.tile_rem = tile_rem;
   rp.seed = st->seed;
-  {  // the drain's tail (pt_wavefront.cuh: stage_tail); PTC_TAIL_RAYS overrides the threshold, 0 disables
-    const char *tail_s = getenv("PTC_TAIL_RAYS");  // read per call: measurements sweep it inside one process
-    const long tail_env = tail_s ? atol(tail_s) : -1;
-    rp.tail_rays = (st->flags & PTC_FLAG_NO_TAIL) ? 0u : (tail_env >= 0 ? (uint32_t)tail_env : kTailRays);
-  }
   {  // odd multiplier coprime with the number of 32-pixel rows (= n_my_tiles * 32): a bijection on row indices
     auto gcd = [](uint64_t a, uint64_t b) {
       while (b) {
@@ -303,7 +305,7 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
 
   CK(cudaEventRecord(ev_begin, stream));
   uint64_t launches = 0;
-  static const uint32_t refill = getenv("PTC_REFILL") ? (uint32_t)atoi(getenv("PTC_REFILL")) : kRefillLanes;
+  const uint32_t refill = traverse_refill_arg();
   auto is_done = [](const Ctl &c) { return c.n_live[0] == 0 && c.next_path >= c.total_paths; };
   // programmatic dependent launches, unless the per-stage events are wanted (they would sit between the launches) or
   // PTC_PDL=0
