@@ -22,7 +22,7 @@
 // B200 and removed; DESIGN.md section 5 keeps the numbers.)
 //
 // Only Emissive surfaces and the sky carry radiance and both end the path (EmissiveLight::scatter is None), so a path
-// contributes beta * Le exactly once, when it terminates: one float RED triple per path into the film.
+// contributes beta * Le exactly once, when it terminates: one 64-bit integer RED triple per path into the fixed-point film.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -94,6 +94,47 @@ struct TaskQ {
                                // kNoTriHit when the ray is parked, lowered with atomicMin by every lane that worked on the task
   uint32_t *cnt;   // [(rounds + 1) * S]
 };
+
+// The film a render accumulates into: FIXED-POINT radiance sums, so that the image does not depend on the order in which
+// paths terminate (integer addition is associative): the same seed gives the same Vec<u32> bit for bit, run after run,
+// for any pool size, any tile / sample sharding and — with the int64 reduce of ptc_multi_* — any number of GPUs, like the
+// reference, whose per-pixel sum has a fixed order (renderer.rs:93-102).  (fp32 atomics, round 1, moved <1 % of the pixels
+// by one display level from run to run.)  One sample's radiance is rounded to a multiple of 2^-28 (the fp32 RED it
+// replaces rounded to an ulp of the running sum, ~2^-17 for a sum of 100) and must be below 2^24 in magnitude; anything
+// larger, infinite or NaN sets a per-pixel flag field instead and comes out of the conversion as +-inf / NaN, which is
+// what an fp32 sum would hold.  A sum holds 2^35: 2048 samples at the per-sample limit.
+constexpr float kFilmScale = 268435456.0f;     // 2^28
+constexpr float kFilmSampleMax = 16777216.0f;  // 2^24
+struct Film {
+  long long *sum;             // [W*H*3] radiance sums * 2^28
+  unsigned long long *flags;  // [W*H] nine 7-bit fields: channel c NaN -> field c, +inf -> 3 + c, -inf -> 6 + c (fields ADD up in
+                              // the multi-GPU reduce: > 0 means set, good for 127 devices)
+};
+__device__ __forceinline__ void film_add1(const Film &f, uint32_t pixel, int c, float v) {
+  if (fabsf(v) < kFilmSampleMax) {
+    atomicAdd(reinterpret_cast<unsigned long long *>(f.sum + (size_t)pixel * 3 + c), (unsigned long long)__float2ll_rn(v * kFilmScale));
+  } else {
+    const int field = (v != v) ? c : (v > 0.0f ? 3 + c : 6 + c);
+    atomicOr(f.flags + pixel, 1ull << (7 * field));
+  }
+}
+__device__ __forceinline__ void film_add(const Film &f, uint32_t pixel, V3 r) {
+  film_add1(f, pixel, 0, r.x);
+  film_add1(f, pixel, 1, r.y);
+  film_add1(f, pixel, 2, r.z);
+}
+// fixed-point film -> fp32 radiance sum of channel c of a pixel (one rounding)
+__device__ __forceinline__ float film_value(long long sum, unsigned long long flags, int c) {
+  float v = (float)sum * (1.0f / kFilmScale);
+  if (flags) {
+    const bool nan = ((flags >> (7 * c)) & 127ull) != 0ull, pinf = ((flags >> (7 * (3 + c))) & 127ull) != 0ull,
+               ninf = ((flags >> (7 * (6 + c))) & 127ull) != 0ull;
+    if (nan || (pinf && ninf)) v = u2f(0x7fc00000u);
+    else if (pinf) v = INFINITY;
+    else if (ninf) v = -INFINITY;
+  }
+  return v;
+}
 
 // hit1.w: hit << 31 | front_face << 30 | material type << 26 (the shade stage's sort key) | material index
 constexpr uint32_t kHitBit = 0x80000000u, kFrontBit = 0x40000000u, kMatMask = 0x03ffffffu;
@@ -449,7 +490,7 @@ __device__ __forceinline__ uint32_t block_rank(bool flag, uint32_t *s_warp /* [k
 //     with gathers in flight all over the window, compaction in place would overwrite rays that are still to be read.
 // Returns the new ray count of the segment.
 __device__ __forceinline__ uint32_t stage_shade(uint32_t seg, uint32_t n_seg, uint32_t half, Ctl *ctl, const DScene &sc, const RenderParams &rp, const Buffers &b,
-                                                float *accum) {
+                                                const Film &film) {
   __shared__ uint16_t s_perm[kShadeWindow];
   __shared__ uint32_t s_hist[2][16];
   __shared__ uint32_t s_warp[kBlock / 32 + 1];
@@ -546,10 +587,7 @@ __device__ __forceinline__ uint32_t stage_shade(uint32_t seg, uint32_t n_seg, ui
           }
         }
         if (add) {
-          float *px = accum + (size_t)pixel * 3;
-          atomicAdd(px + 0, radiance.x);
-          atomicAdd(px + 1, radiance.y);
-          atomicAdd(px + 2, radiance.z);
+          film_add(film, pixel, radiance);
         }
       }
       // survivors: one shared-memory atomic per warp, no barrier
@@ -679,11 +717,18 @@ __global__ void __launch_bounds__(kBlock, kSegPerSM) k_extend_post(SegRange sr, 
   if (sc.n_objects <= kSmemObjects) stage_post<true>(sr.seg0 + blockIdx.x, sr.n_seg, sc, out, tq, round, t_min, t_max);
   else stage_post<false>(sr.seg0 + blockIdx.x, sr.n_seg, sc, out, tq, round, t_min, t_max);
 }
-__global__ void __launch_bounds__(kBlock, kSegPerSM) k_shade(Ctl *ctl, SegRange sr, DScene sc, RenderParams rp, Buffers b, float *accum) {
+__global__ void __launch_bounds__(kBlock, kSegPerSM) k_shade(Ctl *ctl, SegRange sr, DScene sc, RenderParams rp, Buffers b, Film film) {
   pdl_prologue();
-  stage_shade(sr.seg0 + blockIdx.x, sr.n_seg, sr.half, ctl, sc, rp, b, accum);
+  stage_shade(sr.seg0 + blockIdx.x, sr.n_seg, sr.half, ctl, sc, rp, b, film);
 }
 
+// accum[i] += fp32(film sum i): the end of every render (ptc_render_accumulate ADDS into the caller's fp32 film)
+__global__ void k_film_to_accum(Film film, size_t n_pixels, float *accum) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pixels * 3) return;
+  const size_t px = i / 3;
+  accum[i] += film_value(film.sum[i], film.flags[px], (int)(i - px * 3));
+}
 // out = rgb * scale (renderer.rs:103)
 __global__ void k_scale(const float *in, float *out, size_t n, float scale) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -135,6 +135,8 @@ struct ptc_scene {
   Workspace ws;       // render
   Workspace ws_hook;  // ptc_intersect (kept apart so a parity call never disturbs a render's pool)
   DevBuf<float> w_film, w_film_out;  // ptc_render / ptc_resolve_u32 staging, grow-only
+  DevBuf<long long> film_sum;            // the fixed-point film of the render in flight (pt_wavefront.cuh: Film), grow-only
+  DevBuf<unsigned long long> film_flags;
   float *h_film = nullptr;           // pinned staging for the film's way to the caller's (pageable) buffer, grow-only
   size_t h_film_n = 0;
   DevBuf<uint32_t> w_packed;
@@ -209,11 +211,12 @@ void ensure_ctl(ptc_scene *s) {
   for (auto &e : s->ring_ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 }
 
-// the wavefront loop; adds radiance sums into d_accum on `stream`
+// the wavefront loop; renders into the scene's fixed-point film and then adds its fp32 image into d_accum on `stream`
+// (d_accum == nullptr: the caller takes the fixed-point film itself, ptc_multi_*'s int64 reduce)
 void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_settings *st, float *d_accum,
                        cudaStream_t stream, ptc_stats *stats) {
   require_committed(s);
-  if (!cam || !st || !d_accum) throw std::invalid_argument("null argument");
+  if (!cam || !st) throw std::invalid_argument("null argument");
   if (st->width <= 0 || st->height <= 0 || st->spp <= 0) throw std::invalid_argument("bad render settings");
   if ((int64_t)st->width * st->height > (int64_t)0x3fffffff) throw std::invalid_argument("image too large");
   CK(cudaSetDevice(s->device));
@@ -278,6 +281,12 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
   Ctl init;
   memset(&init, 0, sizeof(init));
   init.total_paths = rp.max_depth > 0 ? (unsigned long long)rp.n_my_tiles * 1024ull * (unsigned long long)rp.n_samples : 0ull;
+  const size_t n_px = (size_t)st->width * st->height;
+  if (s->film_sum.n < n_px * 3) s->film_sum.alloc(n_px * 3);
+  if (s->film_flags.n < n_px) s->film_flags.alloc(n_px);
+  const Film film{s->film_sum.p, s->film_flags.p};
+  CK(cudaMemsetAsync(film.sum, 0, n_px * 3 * sizeof(long long), stream));
+  CK(cudaMemsetAsync(film.flags, 0, n_px * sizeof(unsigned long long), stream));
   CK(cudaMemcpyAsync(s->d_ctl.p, &init, sizeof(Ctl), cudaMemcpyHostToDevice, stream));
   CK(cudaMemsetAsync(bufs[0].cnt, 0, segments * sizeof(uint32_t), stream));
 
@@ -329,7 +338,7 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
     };
     auto run_shade = [&]() {  // reads set `flip`, writes the other one, which the next extend then reads
       if (timing) mark(ST_SHADE);
-      launch_stage(pdl, stream, segments, k_shade, s->d_ctl.p, sr, s->ds, rp, bufs[flip], d_accum);
+      launch_stage(pdl, stream, segments, k_shade, s->d_ctl.p, sr, s->ds, rp, bufs[flip], film);
       launches += 1;
       flip ^= 1;
     };
@@ -369,6 +378,11 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
         }
       }
     }
+  }
+  CK(cudaGetLastError());
+  if (d_accum) {
+    k_film_to_accum<<<(unsigned)((n_px * 3 + 255) / 256), 256, 0, stream>>>(film, n_px, d_accum);
+    launches += 1;
   }
   CK(cudaGetLastError());
   CK(cudaEventRecord(ev_end, stream));
@@ -690,6 +704,7 @@ int ptc_render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_
   require_committed(s);
   // the caller's handle is honoured as given: NULL is the legacy default stream, which orders the film atomics after
   // whatever the caller queued there (a memset of d_accum, a wait on a collective)
+  if (!d_accum) throw std::invalid_argument("null argument");
   render_accumulate(s, cam, st, d_accum, (cudaStream_t)cuda_stream, stats);
   return 0;
   PTC_GUARD_END
@@ -952,10 +967,12 @@ static int multi_render(ptc_multi *m, const ptc_camera *cam, const ptc_render_se
   // Everything that can fail for lack of memory happens before the first thread starts: a worker that dropped out
   // ahead of the collective would leave the other devices waiting in ncclReduce for ever.
   if (n > 1 && m->comms_dead) m->init_comms();
+  const size_t n_px = count / 3;
   for (int i = 0; i < n; i++) {
     ptc_scene *s = m->scenes[(size_t)i];
     CK(cudaSetDevice(s->device));
-    if (s->w_film.n < count) s->w_film.alloc(count);
+    if (s->film_sum.n < count) s->film_sum.alloc(count);
+    if (s->film_flags.n < n_px) s->film_flags.alloc(n_px);
   }
   std::mutex abort_mutex;
   auto work = [&](int i) {
@@ -964,7 +981,6 @@ static int multi_render(ptc_multi *m, const ptc_camera *cam, const ptc_render_se
     bool film_ok = false;
     try {
       CK(cudaSetDevice(s->device));
-      CK(cudaMemsetAsync(s->w_film.p, 0, count * sizeof(float), stream));
       ptc_render_settings mine = *st;
       bool idle = false;
       if (shard_mode == PTC_SHARD_SAMPLES) {  // contiguous, balanced split of the sample range
@@ -977,7 +993,12 @@ static int multi_render(ptc_multi *m, const ptc_camera *cam, const ptc_render_se
         mine.tile_mod = n, mine.tile_rem = i;
       }
       memset(&per[(size_t)i], 0, sizeof(ptc_stats));
-      if (!idle) render_accumulate(s, cam, &mine, s->w_film.p, stream, &per[(size_t)i]);
+      if (idle) {
+        CK(cudaMemsetAsync(s->film_sum.p, 0, count * sizeof(long long), stream));
+        CK(cudaMemsetAsync(s->film_flags.p, 0, n_px * sizeof(unsigned long long), stream));
+      } else {
+        render_accumulate(s, cam, &mine, nullptr, stream, &per[(size_t)i]);  // leaves the shard in the device's fixed-point film
+      }
       film_ok = true;
     } catch (std::exception &e) {
       errors[(size_t)i] = e.what();
@@ -986,12 +1007,17 @@ static int multi_render(ptc_multi *m, const ptc_camera *cam, const ptc_render_se
       if (film_ok && cudaStreamSynchronize(stream) != cudaSuccess) errors[(size_t)i] = "cudaStreamSynchronize failed";
       return;
     }
-    // the single exchange step of the path: sum of the radiance films to devices[0].  A device whose render
-    // failed still takes part, with a zeroed film, so that the others return; if it cannot even do that the
-    // communicators are aborted (and re-created by the next call).
+    // the single exchange step of the path: the films are summed onto devices[0].  The sums are 64-bit
+    // integers, so the reduced film — and the image — is the one-GPU film bit for bit, whatever the number of devices and
+    // the order NCCL adds in.  A device whose render failed still takes part, with a zeroed film, so that the others return;
+    // if it cannot even do that the communicators are aborted (and re-created by the next call).
     try {
-      if (!film_ok) CK(cudaMemsetAsync(s->w_film.p, 0, count * sizeof(float), stream));
-      m->nccl.check(m->nccl.Reduce(s->w_film.p, s->w_film.p, count, ncclFloat, ncclSum, 0, m->comms[(size_t)i], stream), "ncclReduce");
+      if (!film_ok) {
+        CK(cudaMemsetAsync(s->film_sum.p, 0, count * sizeof(long long), stream));
+        CK(cudaMemsetAsync(s->film_flags.p, 0, n_px * sizeof(unsigned long long), stream));
+      }
+      m->nccl.check(m->nccl.Reduce(s->film_sum.p, s->film_sum.p, count, ncclInt64, ncclSum, 0, m->comms[(size_t)i], stream), "ncclReduce(film)");
+      m->nccl.check(m->nccl.Reduce(s->film_flags.p, s->film_flags.p, n_px, ncclUint64, ncclSum, 0, m->comms[(size_t)i], stream), "ncclReduce(flags)");
       CK(cudaStreamSynchronize(stream));
     } catch (std::exception &e) {
       if (errors[(size_t)i].empty()) errors[(size_t)i] = e.what();
@@ -1007,6 +1033,10 @@ static int multi_render(ptc_multi *m, const ptc_camera *cam, const ptc_render_se
     if (!errors[(size_t)i].empty()) throw CudaError("device " + std::to_string(m->devices[(size_t)i]) + ": " + errors[(size_t)i]);
   ptc_scene *root = m->primary;
   CK(cudaSetDevice(root->device));
+  if (root->w_film.n < count) root->w_film.alloc(count);
+  CK(cudaMemsetAsync(root->w_film.p, 0, count * sizeof(float), root->own_stream));
+  k_film_to_accum<<<(unsigned)((count + 255) / 256), 256, 0, root->own_stream>>>(Film{root->film_sum.p, root->film_flags.p}, n_px, root->w_film.p);
+  CK(cudaGetLastError());
   const float inv_spp = 1.0f / (float)st->spp;  // renderer.rs:85
   if (out_rgb) {
     if (root->w_film_out.n < count) root->w_film_out.alloc(count);

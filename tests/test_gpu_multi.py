@@ -21,11 +21,10 @@ def test_multi_single_device_equals_render(pt):
     whole, ws = cs.render(s.camera, st)
     for shard in (pt.SHARD_SAMPLES, pt.SHARD_TILES):
         img, ms = cs.multi([0]).render(s.camera, st, shard)
-        assert np.allclose(img, whole, rtol=1e-5, atol=1e-6) and ms.rays == ws.rays and ms.paths == ws.paths
+        assert np.array_equal(img, whole) and ms.rays == ws.rays and ms.paths == ws.paths
     packed, _ = cs.multi([0]).render_u32(s.camera, st)
     want, _ = cs.render_u32(s.camera, st)
-    ch = lambda a: ((a[:, None] >> np.array([16, 8, 0])) & 255).astype(int)  # noqa: E731
-    assert np.abs(ch(packed) - ch(want)).max() <= 1
+    assert np.array_equal(packed, want)
     with pytest.raises(pt.PtcError):
         cs.multi([0, 0])  # duplicate device
     with pytest.raises(pt.PtcError):
@@ -42,9 +41,10 @@ def test_multi_two_devices_shards_are_invisible(pt):
     for shard in (pt.SHARD_SAMPLES, pt.SHARD_TILES):
         img, ms = m.render(s.camera, st, shard)
         assert ms.paths == ws.paths == 200 * 150 * 8 and ms.rays == ws.rays
-        assert np.allclose(img, whole, rtol=1e-5, atol=1e-6)
+        # the films are reduced as 64-bit integers: the multi-GPU image IS the one-GPU image
+        assert np.array_equal(img, whole)
     # more devices than samples: sample sharding leaves devices idle, the image is still the whole image
     st1 = s.render_settings(width=64, height=48, spp=1, max_depth=4, seed=5)
     a, _ = cs.render(s.camera, st1)
     b, _ = m.render(s.camera, st1, pt.SHARD_SAMPLES)
-    assert np.allclose(a, b, rtol=1e-5, atol=1e-6)
+    assert np.array_equal(a, b)
