@@ -17,8 +17,8 @@ CXXFLAGS := -O3 -std=c++17 -fPIC -ffp-contract=off -fno-fast-math -pthread -Wall
 
 all: $(PKG)/libptcore.so $(PKG)/libpthost.so oracle/liboracle.so tests/hostsim/libhostsim.so
 
-$(PKG)/libptcore.so: $(CSRC)/ptcore.cu $(CSRC)/pt_build.cpp $(HDRS)
-	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(CSRC)/ptcore.cu $(CSRC)/pt_build.cpp -ldl
+$(PKG)/libptcore.so: $(CSRC)/ptcore.cu $(CSRC)/pt_build.cpp $(CSRC)/pt_build_dev.cu $(HDRS)
+	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(CSRC)/ptcore.cu $(CSRC)/pt_build.cpp $(CSRC)/pt_build_dev.cu -ldl
 
 $(PKG)/libpthost.so: $(PKG)/host/pthost.cpp $(PKG)/host/json.hpp include/pthost.h include/ptcore.h
 	$(CXX) $(CXXFLAGS) -shared -o $@ $(PKG)/host/pthost.cpp -lz -ldl

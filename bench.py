@@ -361,7 +361,8 @@ def main():
                     e2e = {"value": mst.paths * args.steps / tot / 1e3, "unit": "Mpaths/s", "h2d_bytes_per_step": h2d * world,
                            "d2h_bytes_per_step": h * w * 4 + 64 * world * (1 + spp // 8), "ms_per_step": tot / args.steps,
                            "api": "ptc_multi_render_u32 (in-process: one host thread per GPU, one ncclReduce, host Vec<u32> out), "
-                                  "host wall clock, rank 0 only", "film_reduce_bytes": h * w * 12}
+                                  "host wall clock, rank 0 only", "film_reduce_bytes": h * w * (24 + 8),
+                           "film_reduce_note": "fixed-point film: 3 x int64 sums + one 64-bit flag word per pixel"}
                     del m
                 except Exception as ex:  # noqa: BLE001 — report, do not lose the whole line
                     e2e = dict(e2e_ranks, inprocess_error=str(ex))
@@ -393,7 +394,11 @@ def build_line(args, pt, torch, scene, cs, label, local, world, value, ms_total,
     shade_ms = sum(s.shade_ms for s in stats)
     render_ms = sum(s.render_ms for s in stats)
     # instrumented build of the same kernels, outside the timed region: wide nodes popped / triangles tested per ray
+    # (work stealing off for this one render: a thief walks subtrees its donor might have culled later, which is not
+    # algorithmic work, and a frame this small is all kernel tail)
+    os.environ["PTC_STEAL"] = "0"
     c = cs.render(cam, scene.render_settings(width=min(w, 1280), height=min(h, 720), spp=4, seed=0, flags=pt.FLAG_COUNTERS))[1]
+    os.environ.pop("PTC_STEAL", None)
     nodes_per_ray, tris_per_ray = c.nodes_visited / c.rays, c.tris_tested / c.rays
     objs = scene.objects
     cost = {pt.OBJ_SPHERE: 25, pt.OBJ_PLANE: 14, pt.OBJ_QUAD: 35, pt.OBJ_CUBE: 80, pt.OBJ_MESH: 64}

@@ -154,6 +154,12 @@ int ptc_scene_set_sky_hdr(ptc_scene *, const float *rgb, int32_t w, int32_t h);
 int ptc_scene_build(ptc_scene *);
 /* Flatten + build + upload to CUDA device `device`.  Fails with PTC_E_CUDA when there is no device. */
 int ptc_scene_commit(ptc_scene *, int device);
+/* Same with options.  PTC_COMMIT_FAST_BUILD: flatten the meshes entirely on the device — the reference's own median-split
+ * tree (src/acceleration/bvh.rs:15-76), which has to be restated anyway for the dead-triangle mask, doubles as the
+ * traversal tree: 2 M triangles commit in ~0.2 s instead of ~1 s, the render is ~20 % slower than through the default
+ * SAH tree (host-built from the device-restated mask).  Results (hit records, images) are identical either way. */
+enum { PTC_COMMIT_FAST_BUILD = 1 };
+int ptc_scene_commit_ex(ptc_scene *, int device, int flags);
 int ptc_scene_mesh_info(const ptc_scene *, int object, ptc_mesh_info *info, uint8_t *dead /* n or NULL */,
                         int32_t *order /* n or NULL */);
 

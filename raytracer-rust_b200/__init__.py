@@ -22,6 +22,7 @@ PTC_OK, PTC_E_INVALID, PTC_E_CUDA, PTC_E_NOMEM, PTC_E_STATE = 0, -1, -2, -3, -4
 MAT_LAMBERT, MAT_LAMBERT_CHECKER, MAT_METAL, MAT_DIELECTRIC, MAT_EMISSIVE, MAT_PLASTIC, MAT_ROUGH_CONDUCTOR, MAT_NULL = range(8)
 DIST_GGX, DIST_BECKMANN = 0, 1
 FLAG_COUNTERS, FLAG_TIMING = 1, 2
+COMMIT_FAST_BUILD = 1
 LOAD_INFINITE_SPHERE_SKY, LOAD_WO3_STRIDE16, LOAD_SKIP_UNKNOWN = 1, 2, 4
 OBJ_SPHERE, OBJ_PLANE, OBJ_QUAD, OBJ_CUBE, OBJ_MESH = range(5)
 
@@ -137,6 +138,7 @@ def core():
     L.ptc_scene_set_sky_hdr.argtypes = [_vp, _F, C.c_int32, C.c_int32]
     L.ptc_scene_build.argtypes = [_vp]
     L.ptc_scene_commit.argtypes = [_vp, C.c_int]
+    L.ptc_scene_commit_ex.argtypes = [_vp, C.c_int, C.c_int]
     L.ptc_scene_mesh_info.argtypes = [_vp, C.c_int, C.POINTER(MeshInfo), _vp, _vp]
     L.ptc_render.argtypes = [_vp, C.POINTER(Camera), C.POINTER(RenderSettings), _F, C.POINTER(Stats)]
     L.ptc_render_u32.argtypes = [_vp, C.POINTER(Camera), C.POINTER(RenderSettings), _vp, C.POINTER(Stats)]
@@ -499,8 +501,9 @@ class CoreScene:
         _ck(core().ptc_scene_build(self._h))
         return self
 
-    def commit(self, device=0):
-        _ck(core().ptc_scene_commit(self._h, device))
+    def commit(self, device=0, fast_build=False):
+        """fast_build: PTC_COMMIT_FAST_BUILD — flatten the meshes entirely on the device (quick commit, slower traversal)."""
+        _ck(core().ptc_scene_commit_ex(self._h, device, COMMIT_FAST_BUILD if fast_build else 0))
         self.device = device
         return self
 

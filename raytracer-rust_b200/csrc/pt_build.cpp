@@ -584,9 +584,11 @@ void build_mesh(MeshBuild &m, int threads) {
     const float *t = tri_ptr(m, i);
     for (int a = 0; a < 3; a++) cen[(size_t)i * 3 + a] = ((t[a] + t[3 + a]) + t[6 + a]) * (1.0f / 3.0f);  // bvh.rs:46
   }
-  m.dead.assign((size_t)n, 0);
-  m.order.assign((size_t)n, 0);
-  {
+  if (!m.ref_done) {
+    m.dead.assign((size_t)n, 0);
+    m.order.assign((size_t)n, 0);
+  }
+  if (!m.ref_done) {
     std::vector<int64_t> idx((size_t)n);
     for (int64_t i = 0; i < n; i++) idx[(size_t)i] = i;
     RefCtx rc;

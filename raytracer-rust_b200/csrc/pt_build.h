@@ -25,6 +25,7 @@ struct MeshBuild {
   std::vector<int32_t> order;  // n: position in the reference's DFS leaf order
   int64_t ref_nodes = 0, ref_leaves = 0, live = 0;
   int32_t ref_depth = 0;
+  bool ref_done = false;  // step 1 already done elsewhere (pt_build_dev.cu): build_mesh starts at step 2
 
   // steps 2-3
   std::vector<Node8> nodes;

@@ -103,6 +103,8 @@ extern "C" {
     pub fn ptc_scene_set_sky_hdr(s: *mut ptc_scene, rgb: *const f32, w: i32, h: i32) -> c_int;
     pub fn ptc_scene_build(s: *mut ptc_scene) -> c_int;
     pub fn ptc_scene_commit(s: *mut ptc_scene, device: c_int) -> c_int;
+    /// flags: PTC_COMMIT_FAST_BUILD = 1 (flatten meshes entirely on the device: quick commit, slower traversal)
+    pub fn ptc_scene_commit_ex(s: *mut ptc_scene, device: c_int, flags: c_int) -> c_int;
     pub fn ptc_render(s: *mut ptc_scene, cam: *const ptc_camera, st: *const ptc_render_settings, out_rgb: *mut f32,
                       stats: *mut ptc_stats) -> c_int;
     pub fn ptc_render_u32(s: *mut ptc_scene, cam: *const ptc_camera, st: *const ptc_render_settings, out_u32: *mut u32,
