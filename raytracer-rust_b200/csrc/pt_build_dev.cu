@@ -53,6 +53,29 @@ struct Buf {
   Buf &operator=(const Buf &) = delete;
 };
 
+// Temporaries come out of ONE allocation per build step: cudaMalloc / cudaFree synchronise the device and their cost
+// varies by an order of magnitude from call to call (measured: 137 to 495 ms for the same 2 M-triangle commit with ~25
+// separate buffers), which is the same order as the whole build.
+struct Arena {
+  char *base = nullptr;
+  size_t size = 0, used = 0;
+  explicit Arena(size_t bytes) : size(bytes) { CKB(cudaMalloc(&base, std::max<size_t>(bytes, 256))); }
+  ~Arena() {
+    if (base) cudaFree(base);
+  }
+  Arena(const Arena &) = delete;
+  Arena &operator=(const Arena &) = delete;
+  static size_t need(size_t count, size_t elem) { return (count * elem + 255) & ~(size_t)255; }
+  template <typename T>
+  T *get(size_t count) {
+    const size_t b = need(std::max<size_t>(count, 1), sizeof(T));
+    if (used + b > size) throw std::runtime_error("pt_build_dev: arena too small");
+    T *p = reinterpret_cast<T *>(base + used);
+    used += b;
+    return p;
+  }
+};
+
 constexpr int kThreads = 256;
 inline unsigned blocks_for(size_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
 
@@ -511,29 +534,39 @@ void build_mesh_device(MeshBuild &m, DevMeshBuffers &out, DevBuildTiming *timing
   cudaStream_t stream = nullptr;  // legacy default stream: the build is a synchronous host call
 
   // ---- upload
-  Buf<float> d_tris((size_t)n * 12);
+  int sort_levels = 0;  // levels of the reference tree that still have a node to split
+  while (sort_levels < 25 && (((uint64_t)n + ((1ull << sort_levels) - 1)) >> sort_levels) > 4ull) sort_levels++;
+  size_t temp_bytes = 0;
+  {
+    cub::DoubleBuffer<unsigned long long> kb(nullptr, nullptr);
+    cub::DoubleBuffer<uint32_t> vb(nullptr, nullptr);
+    CKB(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, kb, vb, (int)n, 0, 64, stream));
+  }
+  const size_t segb_count = ((size_t)1 << sort_levels) * 6;
+  Arena a1(Arena::need((size_t)n * 12, 4) + Arena::need((size_t)n * 3, 4) + Arena::need((size_t)n * 6, 4) + 2 * Arena::need(n, 4) +
+           2 * Arena::need(n, 8) + 2 * Arena::need(n, 1) + Arena::need(n, 4) + Arena::need(segb_count, 4) + Arena::need(temp_bytes, 1) + 4096);
+  struct P {
+    float *p;
+  } d_tris{a1.get<float>((size_t)n * 12)}, d_cen{a1.get<float>((size_t)n * 3)}, d_tbox{a1.get<float>((size_t)n * 6)};
+  struct PU {
+    uint32_t *p;
+  } d_idx[2] = {{a1.get<uint32_t>(n)}, {a1.get<uint32_t>(n)}}, d_segb{a1.get<uint32_t>(segb_count)};
+  struct PK {
+    unsigned long long *p;
+  } d_keys[2] = {{a1.get<unsigned long long>(n)}, {a1.get<unsigned long long>(n)}};
+  struct PB {
+    uint8_t *p;
+  } d_dead{a1.get<uint8_t>(n)}, d_dead_pos{a1.get<uint8_t>(n)}, d_temp{a1.get<uint8_t>(temp_bytes)};
+  struct PI {
+    int32_t *p;
+  } d_order{a1.get<int32_t>(n)};
   CKB(cudaMemcpyAsync(d_tris.p, m.tris.data(), (size_t)n * 48, cudaMemcpyHostToDevice, stream));
-  Buf<float> d_cen((size_t)n * 3), d_tbox((size_t)n * 6);
-  Buf<uint32_t> d_idx[2] = {Buf<uint32_t>(n), Buf<uint32_t>(n)};
-  Buf<unsigned long long> d_keys[2] = {Buf<unsigned long long>(n), Buf<unsigned long long>(n)};
-  Buf<uint8_t> d_dead(n), d_dead_pos(n);
-  Buf<int32_t> d_order(n);
   k_tri_prepare<<<blocks_for(n), kThreads, 0, stream>>>(d_tris.p, n, d_cen.p, d_tbox.p, d_idx[0].p, d_dead.p);
   CKB(cudaGetLastError());
   CKB(cudaStreamSynchronize(stream));
   const auto t1 = now();
 
   // ---- step 1: the reference tree, one level per pass
-  int sort_levels = 0;  // levels that still have a node to split
-  while (sort_levels < 25 && (((uint64_t)n + ((1ull << sort_levels) - 1)) >> sort_levels) > 4ull) sort_levels++;
-  Buf<uint32_t> d_segb(((size_t)1 << sort_levels) * 6);
-  size_t temp_bytes = 0;
-  {
-    cub::DoubleBuffer<unsigned long long> kb(d_keys[0].p, d_keys[1].p);
-    cub::DoubleBuffer<uint32_t> vb(d_idx[0].p, d_idx[1].p);
-    CKB(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, kb, vb, (int)n, 0, 64, stream));
-  }
-  Buf<uint8_t> d_temp(temp_bytes);
   int cur = 0;
   for (int L = 0; L <= sort_levels; L++) {
     const size_t segs = (size_t)1 << L;
@@ -619,33 +652,42 @@ void build_mesh_device(MeshBuild &m, DevMeshBuffers &out, DevBuildTiming *timing
   const Structure st = gen_structure(n, R);
   const uint32_t n_nodes = (uint32_t)st.nodes.size(), n_levels = (uint32_t)st.level_first.size() - 1;
   const auto t3 = now();
-  Buf<WNode> d_wn(n_nodes);
-  Buf<uint32_t> d_live(live_tri.size());
+  uint32_t widest = 0;
+  for (uint32_t l = 0; l < n_levels; l++) widest = std::max(widest, st.level_first[l + 1] - st.level_first[l]);
+  size_t scan_bytes = 0;
+  CKB(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)widest, stream));
+  Arena a2(Arena::need(n_nodes, sizeof(WNode)) + Arena::need(live_tri.size(), 4) + Arena::need(st.quads.size(), 4) + Arena::need(n_nodes, sizeof(Box)) +
+           4 * Arena::need(widest, 4) + Arena::need(scan_bytes, 1) + 8192);
+  struct PW {
+    WNode *p;
+  } d_wn{a2.get<WNode>(n_nodes)};
+  PU d_live{a2.get<uint32_t>(live_tri.size())};
   CKB(cudaMemcpyAsync(d_wn.p, st.nodes.data(), (size_t)n_nodes * sizeof(WNode), cudaMemcpyHostToDevice, stream));
   CKB(cudaMemcpyAsync(d_live.p, live_tri.data(), live_tri.size() * 4, cudaMemcpyHostToDevice, stream));
   if (!st.quads.empty()) {
-    Buf<uint32_t> d_quads(st.quads.size());
+    PU d_quads{a2.get<uint32_t>(st.quads.size())};
     CKB(cudaMemcpyAsync(d_quads.p, st.quads.data(), st.quads.size() * 4, cudaMemcpyHostToDevice, stream));
     k_pair_quads<<<blocks_for(st.quads.size()), kThreads, 0, stream>>>(d_quads.p, (uint32_t)st.quads.size(), d_live.p, d_tris.p);
     CKB(cudaGetLastError());
-    CKB(cudaStreamSynchronize(stream));  // d_quads goes out of scope
   }
-  Buf<Box> d_box(n_nodes);
+  struct PX {
+    Box *p;
+  } d_box{a2.get<Box>(n_nodes)};
   Buf<float4> d_nodes((size_t)n_nodes * 5), d_tri48((size_t)std::max(st.n_tri_records, 1u) * 3);
-  Buf<float> d_root(6);
-  Buf<int> d_err(1);
+  struct PF {
+    float *p;
+  } d_root{a2.get<float>(6)};
+  struct PE {
+    int *p;
+  } d_err{a2.get<int>(1)};
   CKB(cudaMemsetAsync(d_err.p, 0, sizeof(int), stream));
   for (uint32_t l = n_levels; l-- > 0;) {
     const uint32_t first = st.level_first[l], count = st.level_first[l + 1] - first;
     k_boxes_level<<<blocks_for(count), kThreads, 0, stream>>>(d_wn.p, first, count, d_live.p, d_tris.p, d_box.p);
   }
   CKB(cudaGetLastError());
-  uint32_t widest = 0;
-  for (uint32_t l = 0; l < n_levels; l++) widest = std::max(widest, st.level_first[l + 1] - st.level_first[l]);
-  Buf<uint32_t> d_sid[2] = {Buf<uint32_t>(widest), Buf<uint32_t>(widest)}, d_cnt(widest), d_cbase(widest);
-  size_t scan_bytes = 0;
-  CKB(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_cnt.p, d_cbase.p, (int)widest, stream));
-  Buf<uint8_t> d_scan(scan_bytes);
+  PU d_sid[2] = {{a2.get<uint32_t>(widest)}, {a2.get<uint32_t>(widest)}}, d_cnt{a2.get<uint32_t>(widest)}, d_cbase{a2.get<uint32_t>(widest)};
+  PB d_scan{a2.get<uint8_t>(scan_bytes)};
   CKB(cudaMemsetAsync(d_sid[0].p, 0, 4, stream));  // level 0: final position 0 holds structural node 0
   for (uint32_t l = 0; l < n_levels; l++) {
     const uint32_t first = st.level_first[l], count = st.level_first[l + 1] - first;

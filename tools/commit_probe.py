@@ -1,0 +1,12 @@
+import os, sys, time
+sys.path.insert(0, os.getcwd())
+import ptload
+pt = ptload.load()
+os.environ["PTC_BUILD_TIMING"] = "1"
+os.environ["PTC_BUILD"] = "device"
+pt.synthetic_scene(cells=64).to_core().commit(0)
+s = pt.synthetic_scene(cells=1000)
+for i in range(4):
+    t0 = time.perf_counter(); c = s.to_core(); t1 = time.perf_counter(); c.commit(0); t2 = time.perf_counter()
+    print(f"run {i}: to_core {1e3*(t1-t0):.0f} ms, commit {1e3*(t2-t1):.0f} ms", flush=True)
+    t0 = time.perf_counter(); del c; print(f"   destroy {1e3*(time.perf_counter()-t0):.0f} ms", flush=True)
