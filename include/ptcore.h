@@ -83,7 +83,13 @@ typedef struct ptc_render_settings {
 
 enum {
   PTC_FLAG_COUNTERS = 1, /* run the instrumented extend kernel: fills nodes_visited / tris_tested (slower) */
-  PTC_FLAG_TIMING = 2    /* record CUDA events around every extend / shade launch: fills extend_ms / shade_ms */
+  PTC_FLAG_TIMING = 2,   /* record CUDA events around every extend / shade launch: fills extend_ms / shade_ms */
+  PTC_FLAG_NEE = 4       /* next-event estimation + multiple importance sampling (the Tungsten scenes ask for
+                            it with "enable_mis", which the reference's IntegratorConfig ignores, src/tungsten/parser.rs:167-171).
+                            OFF by default: the default integrator is the reference's, sample for sample.  With the flag every
+                            non-specular hit also samples one emissive sphere / quad through a shadow ray, and emitters found
+                            by BSDF sampling are weighted with the power heuristic.  Same expected image, far less noise where
+                            emitters are small (veach-mis).  stats.rays then counts the shadow rays too. */
 };
 
 /* HitRecord (src/hittable.rs:10-16) plus the ids the parity bar is stated on. */

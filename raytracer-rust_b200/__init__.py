@@ -21,7 +21,7 @@ REPO_ROOT = os.path.dirname(_HERE)
 PTC_OK, PTC_E_INVALID, PTC_E_CUDA, PTC_E_NOMEM, PTC_E_STATE = 0, -1, -2, -3, -4
 MAT_LAMBERT, MAT_LAMBERT_CHECKER, MAT_METAL, MAT_DIELECTRIC, MAT_EMISSIVE, MAT_PLASTIC, MAT_ROUGH_CONDUCTOR, MAT_NULL = range(8)
 DIST_GGX, DIST_BECKMANN = 0, 1
-FLAG_COUNTERS, FLAG_TIMING = 1, 2
+FLAG_COUNTERS, FLAG_TIMING, FLAG_NEE = 1, 2, 4
 COMMIT_FAST_BUILD = 1
 LOAD_INFINITE_SPHERE_SKY, LOAD_WO3_STRIDE16, LOAD_SKIP_UNKNOWN = 1, 2, 4
 OBJ_SPHERE, OBJ_PLANE, OBJ_QUAD, OBJ_CUBE, OBJ_MESH = range(5)

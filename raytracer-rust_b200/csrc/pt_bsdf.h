@@ -228,6 +228,124 @@ PT_HD bool mat_scatter(const DMaterial &m, V3 ray_d, V3 pos, V3 n, bool front_fa
   }
 }
 
+
+// ---- next-event estimation (PTC_FLAG_NEE; no counterpart in the reference, whose integrator finds emitters by BSDF
+// sampling alone, renderer.rs:19-65).  Everything below is derived FROM the reference's scatter(): the "BSDF" is the one
+// its estimator implies, weight(wi) * pdf(wi), so that light sampling + MIS converges to the very image the reference's
+// integrator converges to.
+//
+// Solid-angle density of the half vector sample_half_vector() draws, as a function of cos(theta_h) = n.h.
+//   Beckmann : tan^2 = -alpha^2 ln u           ->  exp(-tan^2 / alpha^2) / (pi alpha^2 cos^3)       (= D cos)
+//   "Ggx"    : tan^2 = a^2 g(u), a = alpha^2,  g(u) = -ln u / (1 - u), u in [1e-6, 1)  (tungsten/materials.rs:247-262; not the
+//              GGX distribution: tan^2 never falls below a^2).  g is inverted by bisection; |g'| has a removable
+//              singularity at u = 1, hence the series.
+PT_HD float half_vector_pdf(float cos_h, float roughness, int distribution) {
+  if (!(cos_h > 1e-6f)) return 0.0f;
+  const float c2 = cos_h * cos_h;
+  const float tan2 = fmaxf(1.0f - c2, 0.0f) / c2;
+  const float c3 = c2 * cos_h;
+  if (distribution != 0) {
+    const float al2 = roughness * roughness;
+    if (tan2 > 13.8155f * al2) return 0.0f;  // u1 is clamped to >= 1e-6
+    return expf(-tan2 / al2) / (kPi * al2 * c3);
+  }
+  const float a2 = roughness * roughness * roughness * roughness;
+  const float y = tan2 / a2;
+  if (!(y > 1.0f) || y >= 13.8155f) return 0.0f;
+  float lo = 1e-6f, hi = 1.0f;
+  for (int it = 0; it < 26; it++) {
+    const float mid = 0.5f * (lo + hi), w = 1.0f - mid;
+    const float g = w < 0.05f ? 1.0f + w * (0.5f + w * (1.0f / 3.0f + w * 0.25f)) : -logf(mid) / w;
+    if (g > y) lo = mid;  // g decreases
+    else hi = mid;
+  }
+  const float u = 0.5f * (lo + hi), w = 1.0f - u;
+  const float gp = w < 0.1f ? (0.5f + w * (1.0f / 6.0f + w * (1.0f / 12.0f))) / u : (w + u * logf(u)) / (u * w * w);
+  return 1.0f / (kPi * a2 * c3 * gp);
+}
+
+PT_HD float plastic_reflect_prob(const DMaterial &m, V3 ray_d, V3 n) {  // tungsten/materials.rs:33-45, as in mat_scatter
+  const float dn = dot(ray_d, n);
+  const float cosine = dn > 0.0f ? m.ior * dn / length(ray_d) : -dn / length(ray_d);
+  const float r0 = (1.0f - m.ior) / (1.0f + m.ior);
+  const float r0_sq = r0 * r0;
+  return r0_sq + (1.0f - r0_sq) * powi5(1.0f - cosine);
+}
+
+// f * cos of the continuous lobe scatter() samples at this hit, towards wi, and the solid-angle pdf with which scatter()
+// itself generates wi.  false: the material has no lobe light sampling can use (mirror, glass, fuzzed metal, emitters).
+PT_HD bool mat_eval_pdf(const DMaterial &m, V3 ray_d, V3 pos, V3 n, V3 wi, V3 &fcos, float &pdf) {
+  fcos = v3(0, 0, 0);
+  pdf = 0.0f;
+  const float c = dot(n, wi);
+  switch (m.type) {
+    case 0:
+    case 1: {  // cosine-weighted hemisphere (n + unit vector), weight = albedo
+      if (!(c > 0.0f)) return true;
+      pdf = c * (1.0f / kPi);
+      fcos = (m.type == 0 ? v3(m.albedo[0], m.albedo[1], m.albedo[2]) : checker_value(m, pos)) * pdf;
+      return true;
+    }
+    case 5: {  // diffuse branch, taken with probability 1 - reflect_prob, weight = albedo
+      if (!(c > 0.0f)) return true;
+      pdf = (1.0f - plastic_reflect_prob(m, ray_d, n)) * c * (1.0f / kPi);
+      fcos = v3(m.albedo[0], m.albedo[1], m.albedo[2]) * pdf;
+      return true;
+    }
+    case 6: {  // weight = albedo F G (v.h) / (n.v n.h + 1e-4), l = reflect(-v, h), pdf(l) = p_h / (4 v.h)
+      if (!(c > 0.0f)) return true;
+      const V3 v = -normalized(ray_d);
+      const V3 hv = normalized(v + wi);
+      const float n_dot_v = fmaxf(dot(n, v), 0.0f), n_dot_h = fmaxf(dot(n, hv), 0.0f), v_dot_h = fmaxf(dot(v, hv), 0.0f);
+      if (!(v_dot_h > 1e-6f)) return true;
+      const float ph = half_vector_pdf(n_dot_h, m.roughness, m.distribution);
+      if (!(ph > 0.0f)) return true;
+      pdf = ph / (4.0f * v_dot_h);
+      const float g = m.distribution == 0
+                          ? ggx_g1(n_dot_v, m.roughness) * ggx_g1(c, m.roughness)
+                          : 1.0f / (1.0f + beckmann_lambda(m.roughness, n_dot_v) + beckmann_lambda(m.roughness, c));
+      const V3 fr = fresnel_conductor(v_dot_h, v3(m.eta[0], m.eta[1], m.eta[2]), v3(m.k[0], m.k[1], m.k[2]));
+      const float den = n_dot_v * n_dot_h + kEps;
+      if (den > kEps) fcos = v3(m.albedo[0], m.albedo[1], m.albedo[2]) * fr * (g * v_dot_h / den * pdf);
+      return true;
+    }
+    default:
+      return false;
+  }
+}
+// pdf of the direction scatter() just produced with uniforms u4, or -1 when it came from a delta / unsupported lobe
+PT_HD float mat_sampled_pdf(const DMaterial &m, V3 ray_d, V3 pos, V3 n, const float *u4, V3 wi) {
+  if (m.type == 5 && u4[0] < plastic_reflect_prob(m, ray_d, n)) return -1.0f;  // the mirror branch
+  V3 fcos;
+  float pdf;
+  if (!mat_eval_pdf(m, ray_d, pos, n, wi, fcos, pdf)) return -1.0f;
+  return pdf;
+}
+
+// A point on light L seen from x: direction, distance and solid-angle pdf (uniform over the light's area; the emitters are
+// two-sided, material.rs:188-190).
+PT_HD bool light_sample(const DLight &L, V3 x, float u0, float u1, V3 &wi, float &dist, float &pdf) {
+  V3 y, nl;
+  if (L.type == OBJ_SPHERE) {
+    nl = sphere_point(u0, u1);
+    y = v3(L.f[0], L.f[1], L.f[2]) + nl * L.f[3];
+  } else {
+    y = v3(L.f[0], L.f[1], L.f[2]) + v3(L.f[3], L.f[4], L.f[5]) * u0 + v3(L.f[6], L.f[7], L.f[8]) * u1;
+    nl = v3(L.f[9], L.f[10], L.f[11]);
+  }
+  const V3 d = y - x;
+  const float d2 = length_squared(d);
+  if (!(d2 > 1e-12f)) return false;
+  dist = sqrtf(d2);
+  wi = d * (1.0f / dist);
+  const float cos_l = fabsf(dot(nl, wi));
+  if (!(cos_l > 1e-6f)) return false;
+  pdf = d2 / (cos_l * L.area);
+  return true;
+}
+// the same density for a point of L that a BSDF-sampled ray hit at distance `dist` under |cos| = cos_l
+PT_HD float light_pdf(const DLight &L, float dist, float cos_l) { return cos_l > 1e-6f ? dist * dist / (cos_l * L.area) : 0.0f; }
+
 // Sky / background for a ray that missed everything (renderer.rs:38-63)
 PT_HD uint32_t f32_as_u32_sat(float f) {  // Rust `as u32`
   if (!(f > 0.0f)) return 0u;

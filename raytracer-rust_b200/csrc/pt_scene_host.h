@@ -31,6 +31,7 @@ struct HostScene {
   std::vector<std::unique_ptr<MeshBuild>> meshes;
   std::vector<float> sky;
   int32_t sky_w = 0, sky_h = 0;
+  std::vector<DLight> lights;  // filled by build_all
 
   int add_material(const ptc_material *m) {
     if (m->type < PTC_MAT_LAMBERT || m->type > PTC_MAT_NULL) throw std::invalid_argument("unknown material type");
@@ -112,8 +113,35 @@ struct HostScene {
       if (!m->built) build_mesh(*m);
     for (auto &m : meshes)
       if (m->wide_depth + 2 > kTraversalStack) throw std::runtime_error("wide BVH deeper than the traversal stack");
-    if (materials.size() > (size_t)1 << 26) throw std::runtime_error("more than 2^26 materials");
-    for (DObject &o : objects) o.mat_type = materials[(size_t)o.material].type;
+    if (materials.size() > (size_t)1 << 20) throw std::runtime_error("more than 2^20 materials");
+    // emitters next-event estimation can sample: emissive spheres and quads, in object order
+    lights.clear();
+    for (size_t k = 0; k < objects.size(); k++) {
+      DObject &o = objects[k];
+      const DMaterial &m = materials[(size_t)o.material];
+      int32_t light_id = 0;
+      const bool emits = m.type == PTC_MAT_EMISSIVE && (m.albedo[0] != 0.0f || m.albedo[1] != 0.0f || m.albedo[2] != 0.0f);
+      if (emits && (o.type == OBJ_SPHERE || o.type == OBJ_QUAD) && (int)lights.size() < kMaxLights) {
+        DLight l;
+        memset(&l, 0, sizeof(l));
+        l.type = o.type, l.object = (int32_t)k;
+        if (o.type == OBJ_SPHERE) {
+          for (int i = 0; i < 4; i++) l.f[i] = o.f[i];
+          l.area = 4.0f * 3.14159265358979323846f * o.f[3] * o.f[3];
+        } else {
+          for (int i = 0; i < 12; i++) l.f[i] = o.f[i];
+          const float *a = o.f + 3, *b = o.f + 6;
+          const float cx = a[1] * b[2] - a[2] * b[1], cy = a[2] * b[0] - a[0] * b[2], cz = a[0] * b[1] - a[1] * b[0];
+          l.area = std::sqrt(cx * cx + cy * cy + cz * cz);
+        }
+        for (int i = 0; i < 3; i++) l.emission[i] = m.albedo[i];
+        if (l.area > 0.0f) {
+          lights.push_back(l);
+          light_id = (int32_t)lights.size();
+        }
+      }
+      o.hit_bits = (m.type << 26) | (light_id << 20) | o.material;
+    }
   }
 };
 

@@ -17,7 +17,8 @@ struct alignas(16) DObject {
   int32_t type;
   int32_t material;
   int32_t mesh;
-  int32_t mat_type;  // DMaterial::type of `material`, filled at commit: the shade stage's sort key rides in the hit record
+  int32_t hit_bits;  // filled at commit: DMaterial::type << 26 | light id << 20 | material — what the extend stage ORs into the
+                     // hit record (the shade stage's sort key and the NEE light of the object ride along with the material)
   float f[32];
 };
 static_assert(sizeof(DObject) == 144, "DObject layout");
@@ -70,13 +71,28 @@ struct DMesh {
   float root_lo[3], root_hi[3];  // padded frame of the root node: a ray that misses it cannot hit any live triangle
 };
 
+// An emitter that next-event estimation can sample (PTC_FLAG_NEE; the reference has no light sampling): emissive spheres
+// and quads.  Other emissive objects are found by BSDF sampling alone, like every emitter in the reference.
+struct alignas(16) DLight {
+  int32_t type;    // OBJ_SPHERE or OBJ_QUAD
+  int32_t object;  // index in the object table
+  float area;      // 4 pi r^2 / |edge0 x edge1|
+  float pad;
+  float f[12];     // sphere: center, radius | quad: base, edge0, edge1, normal
+  float emission[3];
+  float pad2;
+};
+constexpr int kMaxLights = 63;  // light id 1..63 in the hit record's 6 bits; further emitters are simply not sampled
+
 struct DScene {
   const DObject *objects;
   const DMaterial *materials;
   const DMesh *meshes;
   const float *sky;  // w*h*3 floats or nullptr (Scene.skybox_hdr_image, src/scene.rs:9)
+  const DLight *lights;
   int32_t n_objects, n_materials, n_meshes;
   int32_t sky_w, sky_h;
+  int32_t n_lights;
 };
 
 // HitRecord (src/hittable.rs:10-16) + the ids the parity bar is stated on.

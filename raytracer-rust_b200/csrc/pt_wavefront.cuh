@@ -78,6 +78,9 @@ struct Buffers {
   uint32_t cap;   // multiple of kBlock
   // the ray arrays the shade stage writes (survivors + regenerated paths); the host swaps the two sets every iteration
   float4 *nray_o, *nray_d, *nbeta;
+  // PTC_FLAG_NEE only: solid-angle pdf with which the ray's direction was sampled (-1: camera ray / delta lobe), for the MIS
+  // weight of an emitter it may hit; nullptr otherwise
+  float *aux, *naux;
 };
 
 struct ExtendOut {
@@ -136,9 +139,10 @@ __device__ __forceinline__ float film_value(long long sum, unsigned long long fl
   return v;
 }
 
-// hit1.w: hit << 31 | front_face << 30 | material type << 26 (the shade stage's sort key) | material index
-constexpr uint32_t kHitBit = 0x80000000u, kFrontBit = 0x40000000u, kMatMask = 0x03ffffffu;
-constexpr int kTypeShift = 26;
+// hit1.w: hit << 31 | front_face << 30 | material type << 26 (the shade stage's sort key) | light id << 20 | material index
+constexpr uint32_t kHitBit = 0x80000000u, kFrontBit = 0x40000000u, kMatMask = 0x000fffffu;
+constexpr int kTypeShift = 26, kLightShift = 20;  // DObject::hit_bits: type << 26 | NEE light id << 20 | material index
+constexpr uint32_t kShadowBit = 0x80000000u;       // in a pool entry's pixel word: the entry is an NEE shadow ray (see stage_shade)
 
 __device__ __forceinline__ void write_hit(const ExtendOut &out, uint32_t i, const Hit &h) {
   out.b.hit0[i] = make_float4(h.px, h.py, h.pz, h.t);
@@ -176,7 +180,7 @@ __device__ __forceinline__ int scan_objects(const DScene &sc, const DObject *obj
       closest = best.t;
       best.object = k;
       best.triangle = -1;
-      best.material = ob->material | (ob->mat_type << kTypeShift);  // index | type << 26, see write_hit
+      best.material = ob->hit_bits;  // type << 26 | light << 20 | index, see write_hit
     }
   }
   return -1;
@@ -430,7 +434,7 @@ __device__ __forceinline__ void stage_post(uint32_t seg, uint32_t n_seg, const D
           closest = tmp.t;
           best = tmp;
           best.object = k;
-          best.material = ob->material | (ob->mat_type << kTypeShift);  // index | type << 26, see write_hit
+          best.material = ob->hit_bits;  // type << 26 | light << 20 | index, see write_hit
         }
       }
       park = scan_objects(sc, objs, ray, t_min, closest, best, improved, k + 1, mr);
@@ -443,7 +447,7 @@ __device__ __forceinline__ void stage_post(uint32_t seg, uint32_t n_seg, const D
   if (tid == 0) tq.cnt[(uint32_t)(round + 1) * n_seg + seg] = s_ntask;
 }
 
-constexpr int kShadeClasses = 10;  // 0 = miss, 1 + material type (8 types), 9 = no ray (tail of the last window)
+constexpr int kShadeClasses = 11;  // 0 = miss, 1 + material type (8 types), 9 = NEE shadow ray, 10 = no ray (tail of the last window)
 constexpr int kShadeWindow = 2048;                   // rays one block sorts together
 constexpr int kShadeGroups = kShadeWindow / kBlock;  // 32-ray groups each warp shades per window
 
@@ -488,18 +492,28 @@ __device__ __forceinline__ uint32_t block_rank(bool flag, uint32_t *s_warp /* [k
 //     out of L1/L2: no extra DRAM traffic, and no staging buffers, mbarriers or proxy fences;
 //   * survivors are appended at a block-local cursor (one shared-memory atomic per warp) in the OTHER ray buffer:
 //     with gathers in flight all over the window, compaction in place would overwrite rays that are still to be read.
+//
+// NEE = true (PTC_FLAG_NEE): next-event estimation with multiple importance sampling on top of the same loop.  At every
+// hit whose material has a continuous lobe the stage also samples one emitter (uniformly chosen sphere / quad light,
+// uniform point on it) and emits a SHADOW RAY: one more pool entry (pixel word tagged kShadowBit, the distance in the
+// sample field, the MIS-weighted contribution in beta) that goes through the very same extend stages; the next shade adds
+// its contribution to the film if nothing was hit before the light, and drops it.  An emitter reached by BSDF sampling is
+// weighted with the power heuristic against the light pdf of that point (the sampling pdf travels with the ray in `aux`).
+// The path count of a segment is capped at cap / 2 so that paths + their shadow rays always fit.  The estimator's
+// expectation is the plain integrator's (tested): same image, less variance where the lights are small.
 // Returns the new ray count of the segment.
+template <bool NEE>
 __device__ __forceinline__ uint32_t stage_shade(uint32_t seg, uint32_t n_seg, uint32_t half, Ctl *ctl, const DScene &sc, const RenderParams &rp, const Buffers &b,
                                                 const Film &film) {
   __shared__ uint16_t s_perm[kShadeWindow];
   __shared__ uint32_t s_hist[2][16];
   __shared__ uint32_t s_warp[kBlock / 32 + 1];
   __shared__ unsigned long long s_first;
-  __shared__ uint32_t s_avail, s_more, s_w;
+  __shared__ uint32_t s_avail, s_more, s_w, s_wp;
   const uint32_t n = b.cnt[seg], seg_base = seg * b.cap;
   const uint32_t tid = threadIdx.x, lane = tid & 31u;
   const uint32_t lt_mask = (1u << lane) - 1u;
-  if (tid == 0) s_w = 0u;
+  if (tid == 0) s_w = 0u, s_wp = 0u;
   if (tid < 32u) s_hist[0][tid & 15u] = 0u, s_hist[1][tid & 15u] = 0u;
   __syncthreads();
 
@@ -516,6 +530,7 @@ __device__ __forceinline__ uint32_t stage_shade(uint32_t seg, uint32_t n_seg, ui
       if (idx < wn) {
         const uint32_t bits = f2u(__ldg(&b.hit1[win_base + idx]).w);
         key = (bits & kHitBit) ? 1u + ((bits >> kTypeShift) & 15u) : 0u;
+        if (NEE && (f2u(__ldg(&b.ray_o[win_base + idx].w)) & kShadowBit)) key = 9u;
       }
       const uint32_t peers = __match_any_sync(0xffffffffu, key);
       const int leader = __ffs((int)peers) - 1;
@@ -549,33 +564,50 @@ __device__ __forceinline__ uint32_t stage_shade(uint32_t seg, uint32_t n_seg, ui
     for (int g = 0; g < kShadeGroups; g++) {
       const uint32_t p = (uint32_t)g * kBlock + tid;
       if ((uint32_t)g * kBlock >= wn) break;
-      bool alive = false;
-      float4 no, nd, nb;
+      bool alive = false, shadow = false;
+      float4 no, nd, nb, so4, sd4, sb4;
+      float npdf = -1.0f;
       if (p < wn) {
         const uint32_t i = win_base + (uint32_t)s_perm[p];
         const float4 o4 = __ldg(&b.ray_o[i]), d4 = __ldg(&b.ray_d[i]), b4 = __ldg(&b.beta[i]);
         const float4 h1 = __ldg(&b.hit1[i]);
-        const uint32_t pixel = f2u(o4.w), sample = f2u(d4.w), bounce = f2u(b4.w);
+        const uint32_t pixel_word = f2u(o4.w), sample = f2u(d4.w), bounce = f2u(b4.w);
+        const uint32_t pixel = NEE ? (pixel_word & ~kShadowBit) : pixel_word;
         const uint32_t bits = f2u(h1.w);
         const V3 beta = v3(b4.x, b4.y, b4.z);
         const V3 ray_d = v3(d4.x, d4.y, d4.z);
         V3 radiance = v3(0, 0, 0);
         bool add = false;
-        if (!(bits & kHitBit)) {
+        if (NEE && (pixel_word & kShadowBit)) {
+          // a shadow ray: beta is the MIS-weighted contribution, the sample field the distance to the light point.  The light
+          // itself is hit at that distance; anything nearer (by more than the tolerance) occludes.
+          const float t_light = d4.w;
+          if (!(bits & kHitBit) || !(__ldg(&b.hit0[i]).w < t_light * (1.0f - 2e-4f))) radiance = beta, add = true;
+        } else if (!(bits & kHitBit)) {
           radiance = beta * sky_color(sc, ray_d);
           add = true;
         } else {
           const float4 h0 = __ldg(&b.hit0[i]);
           const DMaterial m = sc.materials[bits & kMatMask];
+          const V3 pos = v3(h0.x, h0.y, h0.z), nrm = v3(h1.x, h1.y, h1.z);
           const V3 e = mat_emitted(m);
           if (e.x != 0.0f || e.y != 0.0f || e.z != 0.0f) {
-            radiance = beta * e;
+            float w_mis = 1.0f;
+            if (NEE) {  // power heuristic against the light-sampling pdf of this very point, if the emitter is a sampled light
+              const float pb = b.aux[i];
+              const uint32_t light = (bits >> kLightShift) & 63u;
+              if (pb >= 0.0f && light != 0u) {
+                const float pl = light_pdf(sc.lights[light - 1u], h0.w, fabsf(dot(nrm, ray_d))) * (1.0f / (float)sc.n_lights);
+                w_mis = pb * pb / (pb * pb + pl * pl);
+              }
+            }
+            radiance = beta * e * w_mis;
             add = true;
           }
           const Uniforms4 u = philox_uniforms(rp.seed, pixel, sample, bounce, 0u);
           Ray sc_ray;
           V3 att;
-          if (mat_scatter(m, ray_d, v3(h0.x, h0.y, h0.z), v3(h1.x, h1.y, h1.z), (bits & kFrontBit) != 0u, u.u, sc_ray, att)) {
+          if (mat_scatter(m, ray_d, pos, nrm, (bits & kFrontBit) != 0u, u.u, sc_ray, att)) {
             // trace_ray(scattered, depth - 1): depth 0 returns black (renderer.rs:20-22)
             if (bounce + 1u < (uint32_t)rp.max_depth) {
               alive = true;
@@ -583,6 +615,28 @@ __device__ __forceinline__ uint32_t stage_shade(uint32_t seg, uint32_t n_seg, ui
               no = make_float4(sc_ray.o.x, sc_ray.o.y, sc_ray.o.z, o4.w);
               nd = make_float4(sc_ray.d.x, sc_ray.d.y, sc_ray.d.z, d4.w);
               nb = make_float4(nbeta.x, nbeta.y, nbeta.z, u2f(bounce + 1u));
+              if (NEE) {
+                npdf = mat_sampled_pdf(m, ray_d, pos, nrm, u.u, sc_ray.d);
+                // light sampling: what the NEXT segment could find at an emitter (hence the same depth rule as the continuation)
+                if (sc.n_lights > 0) {
+                  const Uniforms4 ul = philox_uniforms(rp.seed, pixel, sample, bounce, 1u);
+                  const uint32_t li = min((uint32_t)(ul.u[0] * (float)sc.n_lights), (uint32_t)sc.n_lights - 1u);
+                  const DLight L = sc.lights[li];
+                  const V3 so = pos + nrm * kEps;
+                  V3 wi, fcos;
+                  float dist, pl, pb;
+                  if (light_sample(L, so, ul.u[1], ul.u[2], wi, dist, pl) && mat_eval_pdf(m, ray_d, pos, nrm, wi, fcos, pb) &&
+                      (fcos.x > 0.0f || fcos.y > 0.0f || fcos.z > 0.0f)) {
+                    pl *= 1.0f / (float)sc.n_lights;
+                    const float w_mis = pl * pl / (pl * pl + pb * pb);
+                    const V3 c = beta * fcos * v3(L.emission[0], L.emission[1], L.emission[2]) * (w_mis / pl);
+                    shadow = true;
+                    so4 = make_float4(so.x, so.y, so.z, u2f(pixel | kShadowBit));
+                    sd4 = make_float4(wi.x, wi.y, wi.z, dist);
+                    sb4 = make_float4(c.x, c.y, c.z, u2f(bounce + 1u));
+                  }
+                }
+              }
             }
           }
         }
@@ -590,17 +644,29 @@ __device__ __forceinline__ uint32_t stage_shade(uint32_t seg, uint32_t n_seg, ui
           film_add(film, pixel, radiance);
         }
       }
-      // survivors: one shared-memory atomic per warp, no barrier
+      // survivors (and, with NEE, their shadow rays): one shared-memory atomic per warp, no barrier
       const uint32_t amask = __ballot_sync(0xffffffffu, alive);
-      if (amask != 0u) {
+      const uint32_t smask = NEE ? __ballot_sync(0xffffffffu, shadow) : 0u;
+      if ((amask | smask) != 0u) {
         uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&s_w, (uint32_t)__popc(amask));
+        if (lane == 0) {
+          base = atomicAdd(&s_w, (uint32_t)(__popc(amask) + __popc(smask)));
+          if (NEE) atomicAdd(&s_wp, (uint32_t)__popc(amask));
+        }
         base = __shfl_sync(0xffffffffu, base, 0);
         if (alive) {
           const uint32_t slot = seg_base + base + (uint32_t)__popc(amask & lt_mask);
           b.nray_o[slot] = no;
           b.nray_d[slot] = nd;
           b.nbeta[slot] = nb;
+          if (NEE) b.naux[slot] = npdf;
+        }
+        if (NEE && shadow) {
+          const uint32_t slot = seg_base + base + (uint32_t)__popc(amask) + (uint32_t)__popc(smask & lt_mask);
+          b.nray_o[slot] = so4;
+          b.nray_d[slot] = sd4;
+          b.nbeta[slot] = sb4;
+          b.naux[slot] = -1.0f;
         }
       }
     }
@@ -609,6 +675,7 @@ __device__ __forceinline__ uint32_t stage_shade(uint32_t seg, uint32_t n_seg, ui
   }
   __syncthreads();
   uint32_t w = s_w;  // survivors written so far = write cursor inside the segment (same value in every thread)
+  uint32_t wp = NEE ? s_wp : w;  // ... of which paths (the rest are shadow rays)
 
   // ---- regeneration: top the segment up with fresh camera paths.  Path index -> (sample, 32-pixel row of one of this
   // rank's 32x32 tiles, lane): a warp starts 32 horizontally adjacent pixels of one sample (coherent primary rays,
@@ -623,7 +690,9 @@ __device__ __forceinline__ uint32_t stage_shade(uint32_t seg, uint32_t n_seg, ui
       // no more than a fair share of the whole job per block, in whole 32-pixel rows: a render smaller than the pool
       // would otherwise be swallowed by the first few segments and traced by that many blocks
       const unsigned long long share = ((total + n_seg - 1) / n_seg + 31ull) & ~31ull;
-      const uint32_t free_slots = (uint32_t)min((unsigned long long)(b.cap - w), share);
+      // with NEE a path may add a shadow ray at every bounce: paths are capped at half the segment
+      const uint32_t room = NEE ? min(b.cap - w, b.cap / 2u > wp ? b.cap / 2u - wp : 0u) : b.cap - w;
+      const uint32_t free_slots = (uint32_t)min((unsigned long long)room, share);
       unsigned long long first = total;
       if (free_slots > 0 && ctl->next_path < total) first = atomicAdd(&ctl->next_path, (unsigned long long)free_slots);
       s_first = first;
@@ -663,8 +732,10 @@ __device__ __forceinline__ uint32_t stage_shade(uint32_t seg, uint32_t n_seg, ui
         b.nray_o[slot] = make_float4(ray.o.x, ray.o.y, ray.o.z, u2f(pixel));
         b.nray_d[slot] = make_float4(ray.d.x, ray.d.y, ray.d.z, u2f(sample));
         b.nbeta[slot] = make_float4(1.0f, 1.0f, 1.0f, u2f(0u));
+        if (NEE) b.naux[slot] = -1.0f;
       }
       w += total;
+      wp += total;
       __syncthreads();
     }
     // a batch that fell entirely on out-of-image pixels of border tiles must not look like "no paths left"
@@ -717,9 +788,10 @@ __global__ void __launch_bounds__(kBlock, kSegPerSM) k_extend_post(SegRange sr, 
   if (sc.n_objects <= kSmemObjects) stage_post<true>(sr.seg0 + blockIdx.x, sr.n_seg, sc, out, tq, round, t_min, t_max);
   else stage_post<false>(sr.seg0 + blockIdx.x, sr.n_seg, sc, out, tq, round, t_min, t_max);
 }
+template <bool NEE>
 __global__ void __launch_bounds__(kBlock, kSegPerSM) k_shade(Ctl *ctl, SegRange sr, DScene sc, RenderParams rp, Buffers b, Film film) {
   pdl_prologue();
-  stage_shade(sr.seg0 + blockIdx.x, sr.n_seg, sr.half, ctl, sc, rp, b, film);
+  stage_shade<NEE>(sr.seg0 + blockIdx.x, sr.n_seg, sr.half, ctl, sc, rp, b, film);
 }
 
 // accum[i] += fp32(film sum i): the end of every render (ptc_render_accumulate ADDS into the caller's fp32 film)

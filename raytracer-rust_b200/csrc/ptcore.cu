@@ -78,6 +78,7 @@ struct Workspace {
   int rounds = 0;
   DevBuf<float4> ray_o, ray_d, beta, hit0, hit1;
   DevBuf<float4> ray_o2, ray_d2, beta2;  // second set of ray arrays (renders only): k_shade reads one set, writes the other
+  DevBuf<float> aux, aux2;               // PTC_FLAG_NEE only (allocated at the first such render)
   DevBuf<uint32_t> cnt;
   DevBuf<uint2> tq_ray[2];
   DevBuf<float4> tq_o[2], tq_d[2];
@@ -105,9 +106,12 @@ struct Workspace {
     if (want_pingpong) ray_o2.alloc(n), ray_d2.alloc(n), beta2.alloc(n);
   }
   // flip = 0: the stages read set 1 and k_shade writes set 2; flip = 1: the other way round
+  void ensure_aux() {
+    if (aux.n < slots()) aux.alloc(slots()), aux2.alloc(slots());
+  }
   Buffers buffers(int flip = 0) const {
-    if (flip == 0) return Buffers{ray_o.p, ray_d.p, beta.p, hit0.p, hit1.p, cnt.p, cap, ray_o2.p, ray_d2.p, beta2.p};
-    return Buffers{ray_o2.p, ray_d2.p, beta2.p, hit0.p, hit1.p, cnt.p, cap, ray_o.p, ray_d.p, beta.p};
+    if (flip == 0) return Buffers{ray_o.p, ray_d.p, beta.p, hit0.p, hit1.p, cnt.p, cap, ray_o2.p, ray_d2.p, beta2.p, aux.p, aux2.p};
+    return Buffers{ray_o2.p, ray_d2.p, beta2.p, hit0.p, hit1.p, cnt.p, cap, ray_o.p, ray_d.p, beta.p, aux2.p, aux.p};
   }
   TaskQ taskq() const {
     TaskQ q;
@@ -129,6 +133,7 @@ struct ptc_scene {
   DevBuf<DMaterial> d_materials;
   DevBuf<DMesh> d_meshes;
   DevBuf<float> d_sky;
+  DevBuf<DLight> d_lights;
   std::vector<std::unique_ptr<DevBuf<float4>>> mesh_bufs;
   std::vector<DevMeshBuffers> dev_built;  // per mesh: device arrays left behind by the device-side builder (adopted by upload_scene)
   DScene ds;
@@ -251,6 +256,8 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
   if (cap64 * segments > 0x7fffffffull) throw std::invalid_argument("pool_paths too large");
   ensure_ctl(s);
   s->ws.ensure(segments, (uint32_t)cap64, s->mesh_objects, false, true);
+  const bool nee = (st->flags & PTC_FLAG_NEE) != 0;
+  if (nee) s->ws.ensure_aux();
   Buffers bufs[2] = {s->ws.buffers(0), s->ws.buffers(1)};
   bufs[0].cap = bufs[1].cap = (uint32_t)cap64;  // a pool smaller than the allocation simply uses a smaller segment stride
   const TaskQ tq = s->ws.taskq();
@@ -349,7 +356,8 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
     };
     auto run_shade = [&]() {  // reads set `flip`, writes the other one, which the next extend then reads
       if (timing) mark(ST_SHADE);
-      launch_stage(pdl, stream, segments, k_shade, s->d_ctl.p, sr, s->ds, rp, bufs[flip], film);
+      if (nee) launch_stage(pdl, stream, segments, k_shade<true>, s->d_ctl.p, sr, s->ds, rp, bufs[flip], film);
+      else launch_stage(pdl, stream, segments, k_shade<false>, s->d_ctl.p, sr, s->ds, rp, bufs[flip], film);
       launches += 1;
       flip ^= 1;
     };
@@ -522,6 +530,9 @@ void upload_scene(ptc_scene *s, const HostScene &hs, int device) {
   s->ds.materials = s->d_materials.p;
   s->ds.meshes = s->d_meshes.p;
   s->ds.sky = hs.sky.empty() ? nullptr : s->d_sky.p;
+  s->d_lights.upload(hs.lights.data(), hs.lights.size());
+  s->ds.lights = s->d_lights.p;
+  s->ds.n_lights = (int32_t)hs.lights.size();
   s->ds.n_objects = (int32_t)hs.objects.size();
   s->ds.n_materials = (int32_t)hs.materials.size();
   s->ds.n_meshes = (int32_t)dm.size();

@@ -75,6 +75,8 @@ int sim_scene_commit(sim_scene *s, int /*device*/) {
     s->ds.materials = s->hs.materials.data();
     s->ds.meshes = s->dmeshes.data();
     s->ds.sky = s->hs.sky.empty() ? nullptr : s->hs.sky.data();
+    s->ds.lights = s->hs.lights.data();
+    s->ds.n_lights = (int32_t)s->hs.lights.size();
     s->ds.n_objects = (int32_t)s->hs.objects.size();
     s->ds.n_materials = (int32_t)s->hs.materials.size();
     s->ds.n_meshes = (int32_t)s->dmeshes.size();
