@@ -43,7 +43,7 @@ PT_HD bool hit_sphere(const float *f, const Ray &ray, float t_min, float t_max, 
   h.t = root;
   const V3 p = ray_at(ray, root);
   set_pos(h, p);
-  const V3 outward = (p - center) / radius;  // vec3.rs:117-129 would panic for |radius| < 1e-4; the device divides
+  const V3 outward = (p - center) / radius;  // vec3.rs:117-122 panics for |radius| < 1e-4: such spheres are refused by ptc_scene_add_sphere
   set_face_normal(h, ray.d, outward);
   return true;
 }

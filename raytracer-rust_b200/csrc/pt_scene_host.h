@@ -65,6 +65,10 @@ struct HostScene {
     return o;
   }
   int add_sphere(const float c[3], float radius, int material) {
+    // Sphere::hit divides by the radius through Vec3's Div<f32>, which PANICS for |radius| < 1e-4 (src/vec3.rs:117-122,
+    // src/objects/sphere.rs:45): the reference's render aborts at the first hit of such a sphere.  Nothing may unwind
+    // across this boundary, so the sphere is refused when it is added.
+    if (!(std::fabs(radius) >= 1e-4f)) throw std::invalid_argument("sphere radius below 1e-4: a hit would panic in the reference (vec3.rs:117-122)");
     DObject o = blank(OBJ_SPHERE, material);
     o.f[0] = c[0], o.f[1] = c[1], o.f[2] = c[2], o.f[3] = radius;
     objects.push_back(o);

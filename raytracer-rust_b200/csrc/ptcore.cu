@@ -151,6 +151,7 @@ struct ptc_scene {
   Ctl *h_ctl = nullptr;  // pinned ring
   static constexpr int kRing = 4;
   cudaEvent_t ring_ev[kRing] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;  // render_ms brackets, created once (ensure_ctl)
   cudaStream_t own_stream = nullptr;
   std::vector<cudaEvent_t> timing_events;
 
@@ -169,6 +170,8 @@ struct ptc_scene {
     if (h_film) cudaFreeHost(h_film);
     for (auto &e : ring_ev)
       if (e) cudaEventDestroy(e);
+    if (ev_begin) cudaEventDestroy(ev_begin);
+    if (ev_end) cudaEventDestroy(ev_end);
     for (auto &e : timing_events) cudaEventDestroy(e);
     if (own_stream) cudaStreamDestroy(own_stream);
   }
@@ -225,6 +228,8 @@ void ensure_ctl(ptc_scene *s) {
   s->d_ctl.alloc(1);
   CK(cudaMallocHost(&s->h_ctl, sizeof(Ctl) * ptc_scene::kRing));
   for (auto &e : s->ring_ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  CK(cudaEventCreate(&s->ev_begin));
+  CK(cudaEventCreate(&s->ev_end));
 }
 
 // the wavefront loop; renders into the scene's fixed-point film and then adds its fp32 image into d_accum on `stream`
@@ -312,9 +317,7 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
   const bool timing = (st->flags & PTC_FLAG_TIMING) != 0;
   const int rounds = s->mesh_objects;
 
-  cudaEvent_t ev_begin, ev_end;
-  CK(cudaEventCreate(&ev_begin));
-  CK(cudaEventCreate(&ev_end));
+  const cudaEvent_t ev_begin = s->ev_begin, ev_end = s->ev_end;  // owned by the scene: nothing to leak if a launch throws
   size_t tev_used = 0;
   auto tev = [&]() -> cudaEvent_t {
     if (tev_used == s->timing_events.size()) {
@@ -440,8 +443,6 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
     stats->tris_tested = fin.tris;
     stats->mesh_rays = fin.mesh_rays;
   }
-  cudaEventDestroy(ev_begin);
-  cudaEventDestroy(ev_end);
 }
 
 int fail(int code, const std::string &msg) {

@@ -77,6 +77,13 @@ def test_error_codes_and_call_order(pt):
     assert core.ptc_scene_add_mesh(h, None, 0, ident, ident, 0) == pt.PTC_E_INVALID  # mesh_object.rs:30-36
     bad = pt.Material(type=99)
     assert core.ptc_scene_add_material(h, C.byref(bad)) == pt.PTC_E_INVALID
+    # a sphere the reference cannot intersect without panicking (Vec3 / radius with |radius| < 1e-4, vec3.rs:117-122) is
+    # refused at the boundary instead: an error code, never an unwind or a silent division
+    c = (C.c_float * 3)(0, 0, 0)
+    assert core.ptc_scene_add_sphere(h, c, 5e-5, 0) == pt.PTC_E_INVALID and b"panic in the reference" in core.ptc_last_error()
+    assert core.ptc_scene_add_sphere(h, c, -5e-5, 0) == pt.PTC_E_INVALID
+    assert core.ptc_scene_add_sphere(h, c, float("nan"), 0) == pt.PTC_E_INVALID
+    assert core.ptc_scene_add_sphere(h, c, 1e-4, 0) >= 0
     core.ptc_scene_destroy(h)
 
 
