@@ -200,33 +200,87 @@ int32_t sah_build(SahCtx &c, int32_t first, int32_t count, int par_levels) {
   node.box.reset();
   Box3 cb;
   cb.reset();
-  for (int32_t i = first; i < first + count; i++) {
-    node.box.grow(c.pbox[c.prim[i]]);
-    cb.grow(c.pcen + 3 * (size_t)c.prim[i]);
+  // Both passes over the node's triangles (bounds, then the bins of all three axes at once) are split over the threads
+  // this subtree may still use while the node is large: the top three levels of a 2 M-triangle build used to run them on
+  // one thread each, three gather passes per node.
+  const int workers = (par_levels > 0 && count > (1 << 16)) ? std::min(1 << par_levels, 16) : 1;
+  auto for_chunks = [&](auto &&body) {  // body(worker, begin, end)
+    if (workers == 1) {
+      body(0, first, first + count);
+      return;
+    }
+    std::vector<std::thread> th;
+    const int32_t per = (count + workers - 1) / workers;
+    for (int w = 1; w < workers; w++) {
+      const int32_t lo = first + w * per, hi = std::min(first + count, lo + per);
+      if (lo < hi) th.emplace_back([&body, w, lo, hi]() { body(w, lo, hi); });
+    }
+    body(0, first, std::min(first + count, first + per));
+    for (auto &t : th) t.join();
+  };
+  {
+    Box3 nb1[2], *nb = nb1, *cbs = nb1 + 1;  // the common case (one worker) stays off the heap
+    std::vector<Box3> nbv;
+    if (workers > 1) nbv.resize(2 * (size_t)workers), nb = nbv.data(), cbs = nbv.data() + workers;
+    for (int w = 0; w < workers; w++) nb[(size_t)w].reset(), cbs[(size_t)w].reset();
+    for_chunks([&](int w, int32_t lo, int32_t hi) {
+      Box3 x = nb[(size_t)w], y = cbs[(size_t)w];
+      for (int32_t i = lo; i < hi; i++) {
+        x.grow(c.pbox[c.prim[i]]);
+        y.grow(c.pcen + 3 * (size_t)c.prim[i]);
+      }
+      nb[(size_t)w] = x, cbs[(size_t)w] = y;
+    });
+    for (int w = 0; w < workers; w++) {
+      if (nb[(size_t)w].lo[0] <= nb[(size_t)w].hi[0]) node.box.grow(nb[(size_t)w]);
+      if (cbs[(size_t)w].lo[0] <= cbs[(size_t)w].hi[0]) cb.grow(cbs[(size_t)w]);
+    }
   }
   if (count <= kLeafMax) {
     c.nodes[me] = node;
     return me;
   }
+  struct Bins {
+    Box3 bb[3][kBins];
+    int32_t bn[3][kBins];
+  };
+  float kk[3];
+  bool axis_ok[3];
+  for (int a = 0; a < 3; a++) {
+    const float cext = cb.hi[a] - cb.lo[a];
+    axis_ok[a] = cext > 0.0f;
+    kk[a] = axis_ok[a] ? (float)kBins / cext : 0.0f;
+  }
+  Bins wb1, *wb = &wb1;
+  std::vector<Bins> wbv;
+  if (workers > 1) wbv.resize((size_t)workers), wb = wbv.data();
+  for_chunks([&](int w, int32_t lo, int32_t hi) {
+    Bins &B = wb[(size_t)w];
+    for (int a = 0; a < 3; a++)
+      for (int bi = 0; bi < kBins; bi++) B.bb[a][bi].reset(), B.bn[a][bi] = 0;
+    for (int32_t i = lo; i < hi; i++) {
+      const int32_t p = c.prim[i];
+      const Box3 &pb = c.pbox[p];
+      const float *pc = c.pcen + 3 * (size_t)p;
+      for (int a = 0; a < 3; a++) {
+        if (!axis_ok[a]) continue;
+        int bi = (int)((pc[a] - cb.lo[a]) * kk[a]);
+        bi = std::min(std::max(bi, 0), kBins - 1);
+        B.bb[a][bi].grow(pb);
+        B.bn[a][bi]++;
+      }
+    }
+  });
+  for (int w = 1; w < workers; w++)
+    for (int a = 0; a < 3; a++)
+      for (int bi = 0; bi < kBins; bi++)
+        if (wb[(size_t)w].bn[a][bi]) wb[0].bb[a][bi].grow(wb[(size_t)w].bb[a][bi]), wb[0].bn[a][bi] += wb[(size_t)w].bn[a][bi];
   int best_axis = -1, best_split = -1;
   double best_cost = DBL_MAX;
   for (int a = 0; a < 3; a++) {
-    const float cext = cb.hi[a] - cb.lo[a];
-    if (!(cext > 0.0f)) continue;
-    Box3 bb[kBins];
-    int32_t bn[kBins];
-    for (int b = 0; b < kBins; b++) {
-      bb[b].reset();
-      bn[b] = 0;
-    }
-    const float k = (float)kBins / cext;
-    for (int32_t i = first; i < first + count; i++) {
-      const int32_t p = c.prim[i];
-      int b = (int)((c.pcen[3 * (size_t)p + a] - cb.lo[a]) * k);
-      b = std::min(std::max(b, 0), kBins - 1);
-      bb[b].grow(c.pbox[p]);
-      bn[b]++;
-    }
+    if (!axis_ok[a]) continue;
+    const Box3 *bb = wb[0].bb[a];
+    const int32_t *bn = wb[0].bn[a];
     double right_area[kBins];
     int32_t right_n[kBins];
     Box3 acc;
@@ -410,7 +464,10 @@ void plan_children(const std::vector<B2> &b2, const CollapsePlan &p, int32_t n, 
 }
 
 void collapse(const std::vector<B2> &b2, int32_t root, const int32_t *prim, const int32_t *live_ids, MeshBuild &m) {
+  const auto t_plan = std::chrono::steady_clock::now();
   const CollapsePlan plan = plan_collapse(b2, root);
+  if (getenv("PTC_BUILD_TIMING"))
+    fprintf(stderr, "[pt_build] collapse plan %.0f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_plan).count());
   auto is_leaf = [&](int32_t c) { return plan.greedy ? b2[c].left < 0 : plan.leaf[c] != 0; };
   struct Item {
     int32_t b2, wide, depth;

@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""A small workload that touches every kernel — the command compute-sanitizer (memcheck / racecheck) is pointed at:
+"""A small workload that touches every kernel (written for compute-sanitizer, which turned out to be closed on this
+GPU pool; still the quickest whole-library run):
 semesterbild shrunk (mesh: pre / traverse with stealing / post / shade), the Cornell box with NEE (k_shade<true>, shadow
 rays), ptc_intersect, and the device-side mesh build."""
 import os
