@@ -415,12 +415,12 @@ __device__ __forceinline__ void stage_post(uint32_t seg, uint32_t n_seg, const D
       const uint32_t order = (uint32_t)res;
       // the stage is bound by the latency of these gathers: issue all of them before the first use
       const float4 o4 = out.b.ray_o[i], d4 = out.b.ray_d[i];
-      const float h1w = out.b.hit1[i].w, h0w = out.b.hit0[i].w;
+      // closest_so_far travels with the task (the t_max the traversal ran with; == t_max when nothing was hit before the
+      // mesh): a sequential 4-byte read instead of two gathered sectors of the hit record (hit0.w, hit1.w) per task
+      closest = tq.o[par][j].w;
       float4 nq = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
       if (tri_hit) nq = ldg4(sc.meshes[ob->mesh].normals + order);  // normal + original index, by DFS position
       const Ray ray{v3(o4.x, o4.y, o4.z), v3(d4.x, d4.y, d4.z)};
-      const bool any = (f2u(h1w) & kHitBit) != 0u;
-      if (any) closest = h0w;  // == the t_max the traversal ran with
       Hit best;
       best.triangle = -1;
       bool improved = false;
