@@ -368,7 +368,11 @@ def main():
                     e2e = dict(e2e_ranks, inprocess_error=str(ex))
                 store.set("inprocess_done", "1")
             else:
-                store.wait(["inprocess_done"])
+                import datetime
+                try:
+                    store.wait(["inprocess_done"], datetime.timedelta(seconds=300))
+                except Exception:  # noqa: BLE001 — rank 0 is reporting the problem; do not add a second one
+                    pass
         if e2e is None:
             e2e = e2e_ranks
 
