@@ -717,7 +717,7 @@ int ptc_scene_commit_ex(ptc_scene *s, int device, int flags) {
     s->dev_built.assign(s->hs.meshes.size(), DevMeshBuffers());
     for (size_t mi = 0; mi < s->hs.meshes.size(); mi++) {
       MeshBuild &mb = *s->hs.meshes[mi];
-      if (mb.built || force_host || !tie_default) continue;
+      if (mb.built || force_host || !tie_default || mb.n >= ((int64_t)1 << 27)) continue;  // (the device builder's index width)
       if (!fast && mb.n < kDeviceRefMinTriangles) continue;
       CK(cudaSetDevice(device));
       DevBuildTiming tm;
