@@ -37,7 +37,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-DEFAULT_POOL = 3 << 22  # 12 Mi path-pool slots
+DEFAULT_POOL = 3 << 24  # 48 Mi path-pool slots = 11 GB of path state + task queues (C2 / C4 / C5 on B200: 12 Mi 43.8 / 151.8 / 896 ms,
+                        # 24 Mi 43.6 / 149.6 / 880, 48 Mi 43.3 / 146.7 / 869: fewer, fuller iterations)
 
 
 def metric_name(cfg, w, h, spp, depth):
@@ -197,7 +198,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="C2", choices=["C1", "C2", "C3", "C3s", "C4", "C5"])
-    ap.add_argument("--pool", type=int, default=DEFAULT_POOL, help="path-pool slots (C2 on B200: 4 Mi 48.7 ms, 8 Mi 45.9, 12 Mi 45.0, 16 Mi 44.9)")
+    ap.add_argument("--pool", type=int, default=DEFAULT_POOL, help="path-pool slots")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the extra weak-scaling measurement")
     ap.add_argument("--no-inprocess", action="store_true", help="N > 1: skip the in-process ptc_multi_* measurement on rank 0")
