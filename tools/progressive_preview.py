@@ -3,7 +3,8 @@
 src/main.rs:60-75, which only shows the finished frame).  Nothing new in the library is needed: `ptc_render_accumulate`
 ADDS a sample range into a device-resident film, `ptc_resolve_device` packs it with the scale of the samples so far — so a
 host renders the frame in passes and shows (here: saves) the image after each.  Philox is keyed on the global sample index
-and the film is fixed-point per call, so the last pass IS the one-shot render of the same spp, bit for bit.
+so the last pass is the one-shot render of the same spp up to the fp32 rounding of the per-pass film conversions (the
+script prints the difference).
 
   python tools/progressive_preview.py [scene.json] [passes] [spp_per_pass] [out_dir]
 """
