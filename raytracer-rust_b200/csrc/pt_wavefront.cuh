@@ -305,7 +305,9 @@ __device__ __forceinline__ void stage_traverse(uint32_t seg, uint32_t n_seg, Ctl
         if (j < n) {
           const uint32_t slot = seg_base + j;
           const uint2 rk = tq.ray[par][slot];
-          const float4 o4 = tq.o[par][slot], d4 = tq.d[par][slot];
+          // the direction is read exactly once: a streaming load (evict-first) keeps it from pushing BVH nodes out of L1.
+          // (ray / origin records are re-read by k_extend_post; streaming them too cost post what it saved here.)
+          const float4 o4 = tq.o[par][slot], d4 = __ldcs(&tq.d[par][slot]);
           const DMesh *gm = sc.meshes + sc.objects[rk.y].mesh;
           mesh.nodes = gm->nodes;
           mesh.tris = gm->tris;
