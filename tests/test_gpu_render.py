@@ -116,6 +116,16 @@ def test_render_is_ordered_on_the_callers_stream(pt):
         assert np.allclose(got, want, rtol=1e-5, atol=1e-6), float(np.abs(got - want).max())
 
 
+@pytest.mark.parametrize("name,spp", [("C2", 4), ("C4", 2)])
+def test_native_frame_same_stream(pt, name, spp):
+    # BASELINE configs C2 (800x600, depth 30) and C4 (1280x720, depth 16) at their NATIVE frame and bounce limit — only the
+    # sample count is reduced, to what the CPU oracle renders in a second
+    from raytracer_rust_b200 import workloads
+    _, s = workloads.workload(name)
+    w, h, _, depth = s.settings
+    _same_stream(pt, s, w, h, spp, depth, seed=2)
+
+
 def test_config_c1_full_size_same_stream(pt):
     # BASELINE config C1 exactly: Cornell box 256x256, 16 spp, 8 bounces
     s = pt.load_scene_from_json(os.path.join(SCENES, "cornell-box", "scene.json"))
