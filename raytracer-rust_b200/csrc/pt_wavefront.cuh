@@ -48,6 +48,7 @@ struct Ctl {
   unsigned long long nodes, tris, mesh_rays;  // PTC_FLAG_COUNTERS
   uint32_t n_live[2];      // rays alive after the last shade (sum of the segment counts); [0] is used
   uint32_t iterations[2];  // [0] is used
+  uint32_t trav_next[8];   // k_traverse launch i hands out (segment, part) items from trav_next[i & 7] and resets entry (i + 4) & 7
 };
 
 // A kernel launch covers segments [seg0, seg0 + gridDim.x).
@@ -55,6 +56,7 @@ struct SegRange {
   uint32_t seg0;   // first segment of this launch
   uint32_t n_seg;  // segments of the whole pool (stride of the task-count table)
   uint32_t half;   // index into Ctl::n_live / iterations (always 0 today)
+  uint32_t trav_seq, trav_parts;  // k_traverse only: sequence number of the launch, parts every segment's task list is cut into
 };
 
 struct RenderParams {
@@ -269,9 +271,12 @@ __device__ __forceinline__ void stage_pre(uint32_t seg, uint32_t n_seg, const DS
 // scaling.  Split over the idle lanes the same walk is a few steps deep.
 template <bool COUNT>
 __device__ __forceinline__ void stage_traverse(uint32_t seg, uint32_t n_seg, Ctl *ctl, const DScene &sc, const TaskQ &tq, int round,
-                                               float t_min, uint32_t cap, uint32_t refill_arg) {
+                                               float t_min, uint32_t cap, uint32_t refill_arg, uint32_t part = 0u, uint32_t parts = 1u) {
   __shared__ uint32_t s_cur;
-  const uint32_t n = tq.cnt[(uint32_t)round * n_seg + seg], seg_base = seg * cap;
+  // tasks [first, first + n) of the segment: the whole list, or one of `parts` equal cuts of it
+  const uint32_t n_all = tq.cnt[(uint32_t)round * n_seg + seg];
+  const uint32_t first = (uint32_t)((unsigned long long)n_all * part / parts);
+  const uint32_t n = (uint32_t)((unsigned long long)n_all * (part + 1u) / parts) - first, seg_base = seg * cap + first;
   const int par = round & 1;
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t lt_mask = (1u << lane) - 1u;
@@ -782,7 +787,26 @@ template <bool COUNT>
 __global__ void __launch_bounds__(kBlock, kSegPerSM) k_traverse(Ctl *ctl, SegRange sr, DScene sc, TaskQ tq, int round, float t_min,
                                                                 uint32_t cap, uint32_t refill_lanes) {
   pdl_prologue();
-  stage_traverse<COUNT>(sr.seg0 + blockIdx.x, sr.n_seg, ctl, sc, tq, round, t_min, cap, refill_lanes);
+  if (sr.trav_parts <= 1u) {
+    stage_traverse<COUNT>(sr.seg0 + blockIdx.x, sr.n_seg, ctl, sc, tq, round, t_min, cap, refill_lanes);
+    return;
+  }
+  // Heavy meshes, bulk of the render (the host decides): every segment's task list is cut into `trav_parts` items and
+  // the items beyond the first per block are handed out by a counter — a block whose walks were short takes another
+  // item instead of idling until the slowest block of the launch is done (C5: 5-10 % of every traversal launch).
+  // Ownership of the SEGMENT is irrelevant here: a traversal only reads its task and lowers that task's result key.
+  __shared__ uint32_t s_item;
+  if (blockIdx.x == 0 && threadIdx.x == 0) ctl->trav_next[(sr.trav_seq + 4u) & 7u] = gridDim.x;  // no launch nearer than +2 can be running
+  uint32_t *next = &ctl->trav_next[sr.trav_seq & 7u];
+  const uint32_t n_items = sr.n_seg * sr.trav_parts;
+  uint32_t item = blockIdx.x;
+  while (item < n_items) {
+    stage_traverse<COUNT>(sr.seg0 + item % sr.n_seg, sr.n_seg, ctl, sc, tq, round, t_min, cap, refill_lanes, item / sr.n_seg, sr.trav_parts);
+    __syncthreads();
+    if (threadIdx.x == 0) s_item = atomicAdd(next, 1u);
+    __syncthreads();
+    item = s_item;
+  }
 }
 __global__ void __launch_bounds__(kBlock, kSegPerSM) k_extend_post(SegRange sr, DScene sc, ExtendOut out, TaskQ tq, int round, float t_min,
                                                                    float t_max) {

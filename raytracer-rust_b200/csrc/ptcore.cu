@@ -181,6 +181,10 @@ namespace {
 
 constexpr int64_t kDeviceRefMinTriangles = 1 << 17;  // ptc_scene_commit: from this size on the reference BVH is restated on the device
 
+constexpr int64_t kHeavyMeshTriangles = 1 << 19;  // from this many mesh triangles on, k_traverse hands its tasks out in parts (measured:
+                                                  // C5, 2 M triangles, -7 %; the 125 k-triangle teapot +5 %; profiles/r2_ab_travparts.jsonl)
+constexpr int kTravParts = 4;
+
 enum Stage { ST_PRE = 0, ST_TRAVERSE, ST_POST, ST_SHADE, ST_COUNT };
 
 // One stage launch of the render loop: `segments` blocks of kBlock threads, optionally as a programmatic dependent launch
@@ -208,7 +212,7 @@ uint32_t traverse_refill_arg() {
 // can meet.  Returns the number of launches.
 int launch_extend(cudaStream_t stream, uint32_t segments, int rounds, Ctl *ctl, const DScene &ds, const ExtendOut &eo, const TaskQ &tq,
                   float t_min, float t_max, bool counters) {
-  const SegRange sr{0u, segments, 0u};
+  const SegRange sr{0u, segments, 0u, 0u, 1u};
   k_extend_pre<<<segments, kBlock, 0, stream>>>(ctl, sr, ds, eo, tq, t_min, t_max);
   for (int r = 0; r < rounds; r++) {
     if (counters) k_traverse<true><<<segments, kBlock, 0, stream>>>(ctl, sr, ds, tq, r, t_min, eo.b.cap, traverse_refill_arg());
@@ -303,6 +307,7 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
 
   Ctl init;
   memset(&init, 0, sizeof(init));
+  for (uint32_t &v : init.trav_next) v = segments;
   init.total_paths = rp.max_depth > 0 ? (unsigned long long)rp.n_my_tiles * 1024ull * (unsigned long long)rp.n_samples : 0ull;
   const size_t n_px = (size_t)st->width * st->height;
   if (s->film_sum.n < n_px * 3) s->film_sum.alloc(n_px * 3);
@@ -342,7 +347,15 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
   static const bool pdl_on = getenv("PTC_PDL") ? atoi(getenv("PTC_PDL")) != 0 : true;
   const bool pdl = pdl_on && !timing;
   if (init.total_paths != 0) {
-    const SegRange sr{0u, segments, 0u};
+    const SegRange sr{0u, segments, 0u, 0u, 1u};
+    // k_traverse cuts the task lists into parts handed out dynamically while a scene with a heavy mesh is in the bulk of
+    // its render (pt_wavefront.cuh: k_traverse); in the drain the lists are too short for that.  PTC_TRAV_PARTS overrides.
+    int64_t mesh_tris = 0;
+    for (const auto &mb : s->hs.meshes) mesh_tris += mb->n;
+    const char *tp_env = getenv("PTC_TRAV_PARTS");
+    const uint32_t trav_parts_bulk = tp_env ? (uint32_t)std::max(1, atoi(tp_env)) : (mesh_tris >= kHeavyMeshTriangles ? (uint32_t)kTravParts : 1u);
+    uint32_t trav_seq = 0;
+    bool draining = false;  // a snapshot has shown the path supply exhausted
     int flip = 0;  // the ray set the extend stages read
     auto run_extend = [&]() {
       const ExtendOut eo{bufs[flip], nullptr};
@@ -350,8 +363,9 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
       launch_stage(pdl, stream, segments, k_extend_pre, s->d_ctl.p, sr, s->ds, eo, tq, kEps, INFINITY);  // renderer.rs:24
       for (int r = 0; r < rounds; r++) {
         if (timing) mark(ST_TRAVERSE);
-        if (counters) launch_stage(pdl, stream, segments, k_traverse<true>, s->d_ctl.p, sr, s->ds, tq, r, kEps, eo.b.cap, refill);
-        else launch_stage(pdl, stream, segments, k_traverse<false>, s->d_ctl.p, sr, s->ds, tq, r, kEps, eo.b.cap, refill);
+        const SegRange tsr{0u, segments, 0u, trav_seq++, draining ? 1u : trav_parts_bulk};
+        if (counters) launch_stage(pdl, stream, segments, k_traverse<true>, s->d_ctl.p, tsr, s->ds, tq, r, kEps, eo.b.cap, refill);
+        else launch_stage(pdl, stream, segments, k_traverse<false>, s->d_ctl.p, tsr, s->ds, tq, r, kEps, eo.b.cap, refill);
         if (timing) mark(ST_POST);
         launch_stage(pdl, stream, segments, k_extend_post, sr, s->ds, eo, tq, r, kEps, INFINITY);
       }
@@ -396,7 +410,7 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
             finished = true;
             break;
           }
-          if (s->h_ctl[o].next_path >= s->h_ctl[o].total_paths) check_every = 1;
+          if (s->h_ctl[o].next_path >= s->h_ctl[o].total_paths) check_every = 1, draining = true;
         }
       }
     }
