@@ -787,6 +787,8 @@ template <bool COUNT>
 __global__ void __launch_bounds__(kBlock, kSegPerSM) k_traverse(Ctl *ctl, SegRange sr, DScene sc, TaskQ tq, int round, float t_min,
                                                                 uint32_t cap, uint32_t refill_lanes) {
   pdl_prologue();
+  // (every launch, split or not, prepares the hand-out counter of the launch four after it: no launch nearer than +2 can be running)
+  if (blockIdx.x == 0 && threadIdx.x == 0) ctl->trav_next[(sr.trav_seq + 4u) & 7u] = gridDim.x;
   if (sr.trav_parts <= 1u) {
     stage_traverse<COUNT>(sr.seg0 + blockIdx.x, sr.n_seg, ctl, sc, tq, round, t_min, cap, refill_lanes);
     return;
@@ -796,7 +798,6 @@ __global__ void __launch_bounds__(kBlock, kSegPerSM) k_traverse(Ctl *ctl, SegRan
   // item instead of idling until the slowest block of the launch is done (C5: 5-10 % of every traversal launch).
   // Ownership of the SEGMENT is irrelevant here: a traversal only reads its task and lowers that task's result key.
   __shared__ uint32_t s_item;
-  if (blockIdx.x == 0 && threadIdx.x == 0) ctl->trav_next[(sr.trav_seq + 4u) & 7u] = gridDim.x;  // no launch nearer than +2 can be running
   uint32_t *next = &ctl->trav_next[sr.trav_seq & 7u];
   const uint32_t n_items = sr.n_seg * sr.trav_parts;
   uint32_t item = blockIdx.x;

@@ -215,8 +215,9 @@ int launch_extend(cudaStream_t stream, uint32_t segments, int rounds, Ctl *ctl, 
   const SegRange sr{0u, segments, 0u, 0u, 1u};
   k_extend_pre<<<segments, kBlock, 0, stream>>>(ctl, sr, ds, eo, tq, t_min, t_max);
   for (int r = 0; r < rounds; r++) {
-    if (counters) k_traverse<true><<<segments, kBlock, 0, stream>>>(ctl, sr, ds, tq, r, t_min, eo.b.cap, traverse_refill_arg());
-    else k_traverse<false><<<segments, kBlock, 0, stream>>>(ctl, sr, ds, tq, r, t_min, eo.b.cap, traverse_refill_arg());
+    const SegRange tsr{0u, segments, 0u, (uint32_t)r, 1u};
+    if (counters) k_traverse<true><<<segments, kBlock, 0, stream>>>(ctl, tsr, ds, tq, r, t_min, eo.b.cap, traverse_refill_arg());
+    else k_traverse<false><<<segments, kBlock, 0, stream>>>(ctl, tsr, ds, tq, r, t_min, eo.b.cap, traverse_refill_arg());
     k_extend_post<<<segments, kBlock, 0, stream>>>(sr, ds, eo, tq, r, t_min, t_max);
   }
   return 1 + 2 * rounds;
@@ -883,6 +884,7 @@ int ptc_intersect(ptc_scene *s, const float *origins, const float *dirs, int64_t
   d_out.alloc((size_t)n);
   Ctl init;
   memset(&init, 0, sizeof(init));
+  for (uint32_t &v : init.trav_next) v = segments;
   ctl.upload(&init, 1);
   cudaStream_t st = s->own_stream;
   const unsigned nb = (unsigned)((n + 255) / 256);
