@@ -405,18 +405,9 @@ CollapsePlan plan_collapse(const std::vector<B2> &b2, int32_t root) {
   const double c_t = 1.0, c_n = getenv("PTC_SAH_CN") ? atof(getenv("PTC_SAH_CN")) : 1.8;  // ncu: a node step costs ~1.8 triangle tests per lane
   p.cost.assign(b2.size() * 8, 0.0f);
   p.split.assign(b2.size() * 8, 0);
-  std::vector<int32_t> order;  // post-order
-  {
-    std::vector<int32_t> st{root};
-    while (!st.empty()) {
-      const int32_t n = st.back();
-      st.pop_back();
-      order.push_back(n);
-      if (b2[n].left >= 0) st.push_back(b2[n].left), st.push_back(b2[n].right);
-    }
-    std::reverse(order.begin(), order.end());
-  }
-  for (const int32_t n : order) {
+  // The recurrence only looks down, so the subtrees hanging below binary depth 7 are planned in parallel (each in its own
+  // reversed pre-order = children before parents) and the few nodes above them afterwards.
+  auto plan_node = [&](const int32_t n) {
     const B2 &nd = b2[n];
     const double area = nd.box.area();
     float *C = &p.cost[(size_t)n * 8];
@@ -424,7 +415,7 @@ CollapsePlan plan_collapse(const std::vector<B2> &b2, int32_t root) {
     if (nd.left < 0) {
       for (int i = 0; i < 8; i++) C[i] = (float)(area * nd.count * c_t);
       p.leaf[n] = 1;
-      continue;
+      return;
     }
     const float *L = &p.cost[(size_t)nd.left * 8], *R = &p.cost[(size_t)nd.right * 8];
     double D[9];
@@ -445,7 +436,43 @@ CollapsePlan plan_collapse(const std::vector<B2> &b2, int32_t root) {
       if (D[i] < (double)C[i - 2]) C[i - 1] = (float)D[i], S[i - 1] = K[i];
       else C[i - 1] = C[i - 2], S[i - 1] = 0;
     }
+  };
+  auto plan_subtree = [&](const int32_t sub_root) {
+    std::vector<int32_t> order, st{sub_root};
+    while (!st.empty()) {
+      const int32_t n = st.back();
+      st.pop_back();
+      order.push_back(n);
+      if (b2[n].left >= 0) st.push_back(b2[n].left), st.push_back(b2[n].right);
+    }
+    for (size_t i = order.size(); i-- > 0;) plan_node(order[i]);
+  };
+  std::vector<int32_t> top, subs;  // nodes above the cut (pre-order), roots of the subtrees below it
+  {
+    std::vector<std::pair<int32_t, int>> st{{root, 0}};
+    while (!st.empty()) {
+      const auto [n, d] = st.back();
+      st.pop_back();
+      if (d >= 7 || b2[n].left < 0) {
+        subs.push_back(n);
+        continue;
+      }
+      top.push_back(n);
+      st.push_back({b2[n].left, d + 1}), st.push_back({b2[n].right, d + 1});
+    }
   }
+  {
+    const int workers = b2.size() > (1u << 16) ? (int)std::min<size_t>(16, std::max(1u, std::thread::hardware_concurrency())) : 1;
+    std::atomic<size_t> next{0};
+    auto run = [&]() {
+      for (size_t i = next.fetch_add(1); i < subs.size(); i = next.fetch_add(1)) plan_subtree(subs[i]);
+    };
+    std::vector<std::thread> th;
+    for (int w = 1; w < workers; w++) th.emplace_back(run);
+    run();
+    for (auto &t : th) t.join();
+  }
+  for (size_t i = top.size(); i-- > 0;) plan_node(top[i]);
   return p;
 }
 // the children the plan gives to `slots` slots of a wide node for the subtree of n
@@ -472,10 +499,17 @@ void collapse(const std::vector<B2> &b2, int32_t root, const int32_t *prim, cons
   struct Item {
     int32_t b2, wide, depth;
   };
+  struct Rec {
+    int32_t b2, wide, nch;
+    int32_t ch[8];       // children in the order the plan produced them
+    int slot_child[8];   // ... and by slot
+    uint32_t child_base, tri_base;
+  };
   std::vector<Item> queue;
+  std::vector<Rec> recs;
   m.nodes.clear();
   m.tri48.clear();
-  m.nodes.resize(1);
+  size_t n_nodes = 1, n_tris = 0;
   queue.push_back({root, 0, 0});
   m.wide_depth = 0;
   for (size_t qi = 0; qi < queue.size(); qi++) {
@@ -510,6 +544,25 @@ void collapse(const std::vector<B2> &b2, int32_t root, const int32_t *prim, cons
       ch[pick] = b2[p].left;
       ch[nch++] = b2[p].right;
     }
+    // structure only (sequential, cheap): breadth-first numbering, a node's inner children consecutive (provisionally in
+    // CHILD order; the slot order the traversal needs comes from the geometry and is fixed up in parallel below), a
+    // node's leaf triangles consecutive
+    Rec rec;
+    rec.b2 = it.b2, rec.wide = it.wide, rec.nch = nch;
+    rec.child_base = (uint32_t)n_nodes, rec.tri_base = (uint32_t)n_tris;
+    for (int i = 0; i < 8; i++) rec.ch[i] = i < nch ? ch[i] : -1, rec.slot_child[i] = -1;
+    for (int i = 0; i < nch; i++) {
+      if (!is_leaf(ch[i])) queue.push_back({ch[i], (int32_t)n_nodes++, it.depth + 1});
+      else n_tris += (size_t)b2[ch[i]].count;
+    }
+    recs.push_back(rec);
+  }
+  // queue[k].wide == k for every k (breadth-first numbering), so recs[k] describes provisional node k
+  std::vector<uint32_t> final_of(n_nodes, 0u);
+  auto assign_slots = [&](Rec &rc) {
+    const B2 &n = b2[rc.b2];
+    const int nch = rc.nch;
+    const int32_t *ch = rc.ch;
     // Octant-ordered slots: slot s "lives" at corner (s&1 ? +x : -x, s&2 ? +y : -y, s&4 ? +z : -z); the traversal
     // visits slot (ray octant) first.  Greedy assignment on dot(child centre - node centre, corner direction).
     float nc[3];
@@ -526,8 +579,7 @@ void collapse(const std::vector<B2> &b2, int32_t root, const int32_t *prim, cons
         cost[i][s] = d;
       }
     }
-    int slot_child[8];
-    for (int s = 0; s < 8; s++) slot_child[s] = -1;
+    int slot_of_child[8];
     bool child_done[8] = {false, false, false, false, false, false, false, false};
     for (int round = 0; round < nch; round++) {
       int bi = -1, bs = -1;
@@ -535,7 +587,7 @@ void collapse(const std::vector<B2> &b2, int32_t root, const int32_t *prim, cons
       for (int i = 0; i < nch; i++) {
         if (child_done[i]) continue;
         for (int s = 0; s < 8; s++) {
-          if (slot_child[s] >= 0) continue;
+          if (rc.slot_child[s] >= 0) continue;
           if (cost[i][s] > bc) {
             bc = cost[i][s];
             bi = i;
@@ -544,11 +596,48 @@ void collapse(const std::vector<B2> &b2, int32_t root, const int32_t *prim, cons
         }
       }
       child_done[bi] = true;
-      slot_child[bs] = ch[bi];
+      rc.slot_child[bs] = ch[bi];
+      slot_of_child[bi] = bs;
     }
+    // inner child i holds provisional id child_base + (inner children before it in child order); its final id is
+    // child_base + (inner children in lower slots)
+    uint32_t prov = rc.child_base;
+    for (int i = 0; i < nch; i++) {
+      if (is_leaf(ch[i])) continue;
+      uint32_t below = 0;
+      for (int j = 0; j < nch; j++)
+        if (!is_leaf(ch[j]) && slot_of_child[j] < slot_of_child[i]) below++;
+      final_of[prov++] = rc.child_base + below;
+    }
+  };
+  auto for_recs = [&](auto &&body) {
+    const int workers = recs.size() > 4096 ? (int)std::min<size_t>(16, std::max(1u, std::thread::hardware_concurrency())) : 1;
+    std::vector<std::string> errors((size_t)workers);
+    auto run = [&](int w) {
+      try {
+        for (size_t i = (size_t)w; i < recs.size(); i += (size_t)workers) body(recs[i]);
+      } catch (std::exception &e) {
+        errors[(size_t)w] = e.what();
+      }
+    };
+    std::vector<std::thread> th;
+    for (int w = 1; w < workers; w++) th.emplace_back(run, w);
+    run(0);
+    for (auto &t : th) t.join();
+    for (const std::string &e : errors)
+      if (!e.empty()) throw std::runtime_error(e);
+  };
+  for_recs(assign_slots);
+  m.nodes.resize(n_nodes);
+  m.tri48.resize(n_tris);
+  if (getenv("PTC_BUILD_TIMING"))
+    fprintf(stderr, "[pt_build] collapse plan + structure %.0f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_plan).count());
 
+  auto emit = [&](const Rec &rc) {
+    const B2 &n = b2[rc.b2];
+    const int *slot_child = rc.slot_child;
     const QFrame fr = make_frame(n.box);
-    if (it.wide == 0)
+    if (rc.wide == 0)  // the root keeps index 0
       for (int a = 0; a < 3; a++) {
         m.root_lo[a] = fr.origin[a];
         m.root_hi[a] = (float)((double)fr.origin[a] + 255.0 * fr.scale[a]);
@@ -562,9 +651,8 @@ void collapse(const std::vector<B2> &b2, int32_t root, const int32_t *prim, cons
         qhi[a][s] = 0;
       }
     uint32_t imask = 0;
-    const uint32_t child_base = (uint32_t)m.nodes.size();
-    const uint32_t tri_base = (uint32_t)m.tri48.size();
-    int n_inner = 0, tri_off = 0;
+    const uint32_t child_base = rc.child_base, tri_base = rc.tri_base;
+    int tri_off = 0;
     for (int s = 0; s < 8; s++) {
       const int32_t c = slot_child[s];
       if (c < 0) continue;
@@ -572,8 +660,6 @@ void collapse(const std::vector<B2> &b2, int32_t root, const int32_t *prim, cons
       if (!is_leaf(c)) {
         imask |= 1u << s;
         meta[s] = (uint8_t)(0x20 | (24 + s));
-        queue.push_back({c, (int32_t)(child_base + n_inner), it.depth + 1});
-        n_inner++;
       } else {
         const int cnt = cn.count;
         const uint32_t unary = cnt == 1 ? 1u : (cnt == 2 ? 3u : 7u);
@@ -586,7 +672,7 @@ void collapse(const std::vector<B2> &b2, int32_t root, const int32_t *prim, cons
           r.t[0] = make_float4(t[0], t[1], t[2], u2f_host((uint32_t)orig));
           r.t[1] = make_float4(t[3] - t[0], t[4] - t[1], t[5] - t[2], u2f_host((uint32_t)m.order[orig]));
           r.t[2] = make_float4(t[6] - t[0], t[7] - t[1], t[8] - t[2], 0.0f);
-          m.tri48.push_back(r);
+          m.tri48[(size_t)tri_base + (size_t)tri_off + (size_t)k] = r;
         }
         tri_off += cnt;
       }
@@ -601,8 +687,6 @@ void collapse(const std::vector<B2> &b2, int32_t root, const int32_t *prim, cons
         qhi[a][s] = (uint8_t)qh;
       }
     }
-    m.nodes.resize(child_base + n_inner);
-
     auto pack4 = [](const uint8_t *b) -> float {
       return u2f_host((uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24));
     };
@@ -614,8 +698,10 @@ void collapse(const std::vector<B2> &b2, int32_t root, const int32_t *prim, cons
     out.q[2] = make_float4(pack4(qlo[0]), pack4(qlo[0] + 4), pack4(qlo[1]), pack4(qlo[1] + 4));
     out.q[3] = make_float4(pack4(qlo[2]), pack4(qlo[2] + 4), pack4(qhi[0]), pack4(qhi[0] + 4));
     out.q[4] = make_float4(pack4(qhi[1]), pack4(qhi[1] + 4), pack4(qhi[2]), pack4(qhi[2] + 4));
-    m.nodes[it.wide] = out;
-  }
+    m.nodes[(size_t)final_of[(size_t)rc.wide]] = out;
+  };
+  // frames, quantisation and triangle records: independent per wide node
+  for_recs(emit);
   (void)f2u_host;
 }
 
