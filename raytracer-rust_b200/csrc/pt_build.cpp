@@ -192,10 +192,32 @@ struct SahCtx {
 constexpr int kBins = 16;
 constexpr int kLeafMax = 3;  // a leaf slot of a wide node addresses at most 3 triangles
 
-int32_t sah_build(SahCtx &c, int32_t first, int32_t count, int par_levels) {
+// `pbox` / `pcen` / `prim` are the arrays this subtree works on: the mesh-wide ones near the root, private compact copies
+// below kLocalizeCount triangles (see there); `offset` turns positions in `prim` into positions in the mesh-wide list.
+constexpr int32_t kLocalizeCount = 1 << 17;
+int32_t sah_build_view(SahCtx &c, const Box3 *pbox, const float *pcen, int32_t *prim, int32_t offset, bool localized, int32_t first,
+                       int32_t count, int par_levels) {
+  if (!localized && count <= kLocalizeCount && count > 4096) {
+    // From here down the subtree fits a core's cache — if its data are contiguous.  Near the root every pass gathers
+    // boxes and centroids through the permutation (one DRAM miss per triangle, pass and level: what the build spent its
+    // time on); a private copy in current order makes every deeper pass a stream.
+    std::vector<Box3> lbox((size_t)count);
+    std::vector<float> lcen((size_t)count * 3);
+    std::vector<int32_t> lprim((size_t)count), orig((size_t)count);
+    for (int32_t i = 0; i < count; i++) {
+      const int32_t p = prim[first + i];
+      orig[(size_t)i] = p;
+      lbox[(size_t)i] = pbox[p];
+      for (int a = 0; a < 3; a++) lcen[(size_t)i * 3 + a] = pcen[3 * (size_t)p + a];
+      lprim[(size_t)i] = i;
+    }
+    const int32_t r = sah_build_view(c, lbox.data(), lcen.data(), lprim.data(), offset + first, true, 0, count, par_levels);
+    for (int32_t i = 0; i < count; i++) prim[first + i] = orig[(size_t)lprim[(size_t)i]];
+    return r;
+  }
   const int32_t me = c.next.fetch_add(1);
   B2 node;
-  node.first = first;
+  node.first = first + offset;
   node.count = count;
   node.box.reset();
   Box3 cb;
@@ -226,8 +248,8 @@ int32_t sah_build(SahCtx &c, int32_t first, int32_t count, int par_levels) {
     for_chunks([&](int w, int32_t lo, int32_t hi) {
       Box3 x = nb[(size_t)w], y = cbs[(size_t)w];
       for (int32_t i = lo; i < hi; i++) {
-        x.grow(c.pbox[c.prim[i]]);
-        y.grow(c.pcen + 3 * (size_t)c.prim[i]);
+        x.grow(pbox[prim[i]]);
+        y.grow(pcen + 3 * (size_t)prim[i]);
       }
       nb[(size_t)w] = x, cbs[(size_t)w] = y;
     });
@@ -259,9 +281,9 @@ int32_t sah_build(SahCtx &c, int32_t first, int32_t count, int par_levels) {
     for (int a = 0; a < 3; a++)
       for (int bi = 0; bi < kBins; bi++) B.bb[a][bi].reset(), B.bn[a][bi] = 0;
     for (int32_t i = lo; i < hi; i++) {
-      const int32_t p = c.prim[i];
-      const Box3 &pb = c.pbox[p];
-      const float *pc = c.pcen + 3 * (size_t)p;
+      const int32_t p = prim[i];
+      const Box3 &pb = pbox[p];
+      const float *pc = pcen + 3 * (size_t)p;
       for (int a = 0; a < 3; a++) {
         if (!axis_ok[a]) continue;
         int bi = (int)((pc[a] - cb.lo[a]) * kk[a]);
@@ -314,9 +336,9 @@ int32_t sah_build(SahCtx &c, int32_t first, int32_t count, int par_levels) {
     const float k = (float)kBins / cext;
     const float lo = cb.lo[best_axis];
     const int a = best_axis, split = best_split;
-    int32_t *b = c.prim + first, *e = c.prim + first + count;
+    int32_t *b = prim + first, *e = prim + first + count;
     int32_t *m = std::partition(b, e, [&](int32_t p) {
-      int bin = (int)((c.pcen[3 * (size_t)p + a] - lo) * k);
+      int bin = (int)((pcen[3 * (size_t)p + a] - lo) * k);
       bin = std::min(std::max(bin, 0), kBins - 1);
       return bin < split;
     });
@@ -325,17 +347,21 @@ int32_t sah_build(SahCtx &c, int32_t first, int32_t count, int par_levels) {
   }
   int32_t l, r;
   if (par_levels > 0 && count > (1 << 14)) {
-    std::thread th([&]() { l = sah_build(c, first, mid - first, par_levels - 1); });
-    r = sah_build(c, mid, first + count - mid, par_levels - 1);
+    std::thread th([&]() { l = sah_build_view(c, pbox, pcen, prim, offset, localized, first, mid - first, par_levels - 1); });
+    r = sah_build_view(c, pbox, pcen, prim, offset, localized, mid, first + count - mid, par_levels - 1);
     th.join();
   } else {
-    l = sah_build(c, first, mid - first, 0);
-    r = sah_build(c, mid, first + count - mid, 0);
+    l = sah_build_view(c, pbox, pcen, prim, offset, localized, first, mid - first, 0);
+    r = sah_build_view(c, pbox, pcen, prim, offset, localized, mid, first + count - mid, 0);
   }
   node.left = l;
   node.right = r;
   c.nodes[me] = node;
   return me;
+}
+
+int32_t sah_build(SahCtx &c, int32_t first, int32_t count, int par_levels) {
+  return sah_build_view(c, c.pbox, c.pcen, c.prim, 0, false, first, count, par_levels);
 }
 
 // ------------------------------------------------------------------------------------------------------------
