@@ -744,8 +744,13 @@ int ptc_scene_commit_ex(ptc_scene *s, int device, int flags) {
                 tm.download_ms, tm.total_ms, mb.nodes.size(), mb.wide_depth);
     }
   }
+  const auto t_host = std::chrono::steady_clock::now();
   s->hs.build_all();  // host flattening of what is left: reference-BVH dead mask -> SAH -> 8-wide quantised BVH
+  const auto t_up = std::chrono::steady_clock::now();
   upload_scene(s, s->hs, device);
+  if (getenv("PTC_BUILD_TIMING"))
+    fprintf(stderr, "[ptc_scene_commit] host flattening %.1f ms, upload %.1f ms\n", std::chrono::duration<double, std::milli>(t_up - t_host).count(),
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_up).count());
   return 0;
   PTC_GUARD_END
 }

@@ -3,7 +3,9 @@ sys.path.insert(0, os.getcwd())
 import ptload
 pt = ptload.load()
 os.environ["PTC_BUILD_TIMING"] = "1"
-os.environ["PTC_BUILD"] = "device"
+mode = sys.argv[1] if len(sys.argv) > 1 else "device"  # device | host | hybrid (the default of ptc_scene_commit)
+if mode != "hybrid":
+    os.environ["PTC_BUILD"] = mode
 pt.synthetic_scene(cells=64).to_core().commit(0)
 s = pt.synthetic_scene(cells=1000)
 for i in range(4):
