@@ -116,10 +116,11 @@ def test_render_is_ordered_on_the_callers_stream(pt):
         assert np.allclose(got, want, rtol=1e-5, atol=1e-6), float(np.abs(got - want).max())
 
 
-@pytest.mark.parametrize("name,spp", [("C2", 4), ("C4", 2)])
+@pytest.mark.parametrize("name,spp", [("C2", 4), ("C3", 2), ("C4", 2), ("C5", 1)])
 def test_native_frame_same_stream(pt, name, spp):
-    # BASELINE configs C2 (800x600, depth 30) and C4 (1280x720, depth 16) at their NATIVE frame and bounce limit — only the
-    # sample count is reduced, to what the CPU oracle renders in a second
+    # BASELINE configs C2 (800x600, depth 30), C3 (derived teapot, 1280x720, depth 64), C4 (1280x720, depth 16) and C5 (the
+    # full 2,000,000-triangle mesh, 3840x2160, depth 16) at their NATIVE frame and bounce limit — only the sample count is
+    # reduced, to what the CPU oracle renders in a few seconds
     from raytracer_rust_b200 import workloads
     _, s = workloads.workload(name)
     w, h, _, depth = s.settings
