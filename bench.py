@@ -37,8 +37,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-DEFAULT_POOL = 3 << 24  # 48 Mi path-pool slots = 11 GB of path state + task queues (C2 / C4 / C5 on B200: 12 Mi 43.8 / 151.8 / 896 ms,
-                        # 24 Mi 43.6 / 149.6 / 880, 48 Mi 43.3 / 146.7 / 869: fewer, fuller iterations)
+DEFAULT_POOL = 0  # the library's default: the whole job in flight at once if it fits a quarter of the free memory, else 48 Mi slots
 
 
 def metric_name(cfg, w, h, spp, depth):
@@ -486,7 +485,8 @@ def build_line(args, pt, torch, scene, cs, label, local, world, value, ms_total,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": label, "parallelism": f"sample range split x{world} (fixed job)" if world > 1 else "single GPU",
-                   "spp_total": spp, "l2": "256 MiB flush write between timed steps", "pool_paths": args.pool,
+                   "spp_total": spp, "l2": "256 MiB flush write between timed steps", "pool_paths": cs.last_pool_slots(),
+                   "pool_policy": "library default" if args.pool == 0 else "--pool",
                    "rng": "Philox4x32-10 keyed (pixel, sample, bounce)", "commit_s": commit_s},
         "mrays_per_s": rays_all / ms_total / 1e3, "rays_per_path": rays_all / paths_all,
         "e2e": e2e,

@@ -77,7 +77,8 @@ typedef struct ptc_render_settings {
   int32_t sample_end;
   int32_t tile_mod;     /* pixel sharding: only 32x32 tiles with tile_index % tile_mod == tile_rem; 0 = all */
   int32_t tile_rem;
-  int32_t pool_paths;   /* path-pool slots; 0 = default (up to 1<<23, less for small renders) */
+  int32_t pool_paths;   /* path-pool slots; 0 = default: the whole job in flight at once when that fits a quarter of the free
+                           device memory (224 B per slot with meshes), else 48 Mi slots */
   int32_t flags;        /* PTC_FLAG_* */
 } ptc_render_settings;
 
@@ -166,6 +167,8 @@ int ptc_scene_commit(ptc_scene *, int device);
  * SAH tree (host-built from the device-restated mask).  Results (hit records, images) are identical either way. */
 enum { PTC_COMMIT_FAST_BUILD = 1 };
 int ptc_scene_commit_ex(ptc_scene *, int device, int flags);
+/* Path-pool slots the last render on this handle used (what pool_paths = 0 resolved to). */
+int64_t ptc_scene_last_pool_slots(const ptc_scene *);
 int ptc_scene_mesh_info(const ptc_scene *, int object, ptc_mesh_info *info, uint8_t *dead /* n or NULL */,
                         int32_t *order /* n or NULL */);
 

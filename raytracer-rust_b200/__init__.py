@@ -140,6 +140,8 @@ def core():
     L.ptc_scene_commit.argtypes = [_vp, C.c_int]
     L.ptc_scene_commit_ex.argtypes = [_vp, C.c_int, C.c_int]
     L.ptc_scene_mesh_info.argtypes = [_vp, C.c_int, C.POINTER(MeshInfo), _vp, _vp]
+    L.ptc_scene_last_pool_slots.argtypes = [_vp]
+    L.ptc_scene_last_pool_slots.restype = C.c_int64
     L.ptc_render.argtypes = [_vp, C.POINTER(Camera), C.POINTER(RenderSettings), _F, C.POINTER(Stats)]
     L.ptc_render_u32.argtypes = [_vp, C.POINTER(Camera), C.POINTER(RenderSettings), _vp, C.POINTER(Stats)]
     L.ptc_render_accumulate.argtypes = [_vp, C.POINTER(Camera), C.POINTER(RenderSettings), _vp, _vp, C.POINTER(Stats)]
@@ -506,6 +508,9 @@ class CoreScene:
         _ck(core().ptc_scene_commit_ex(self._h, device, COMMIT_FAST_BUILD if fast_build else 0))
         self.device = device
         return self
+
+    def last_pool_slots(self):
+        return int(core().ptc_scene_last_pool_slots(self._h))
 
     def mesh_info(self, obj):
         info = MeshInfo()

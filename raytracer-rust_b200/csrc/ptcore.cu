@@ -139,6 +139,8 @@ struct ptc_scene {
   DScene ds;
   int mesh_objects = 0;  // mesh entries in object_list = extend rounds needed
 
+  int64_t last_pool_slots = 0;  // path-pool slots of the last render (ptc_scene_last_pool_slots)
+  uint64_t pool_budget_bytes = 0;  // what the default pool may occupy: a quarter of the memory free at the first render, at most 48 GiB
   Workspace ws;       // render
   Workspace ws_hook;  // ptc_intersect (kept apart so a parity call never disturbs a render's pool)
   DevBuf<float> w_film, w_film_out;  // ptc_render / ptc_resolve_u32 staging, grow-only
@@ -252,13 +254,38 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
   const int tile_mod = st->tile_mod > 0 ? st->tile_mod : 1;
   const int tile_rem = st->tile_mod > 0 ? st->tile_rem : 0;
   if (tile_rem < 0 || tile_rem >= tile_mod) throw std::invalid_argument("tile_rem out of range");
-  const uint64_t want_paths = (uint64_t)st->width * st->height * (uint64_t)(s_end - s_begin);
+  const bool nee = (st->flags & PTC_FLAG_NEE) != 0;
+  // paths this call starts (its tiles x its samples; border tiles padded to 32 x 32 like the path index space)
+  uint64_t want_paths;
+  {
+    const int tx = (st->width + 31) / 32, ty = (st->height + 31) / 32, nt = tx * ty;
+    const int mine = tile_rem < nt ? (nt - tile_rem + tile_mod - 1) / tile_mod : 0;
+    want_paths = (uint64_t)mine * 1024ull * (uint64_t)(s_end - s_begin);
+  }
   uint64_t pool;
   if (st->pool_paths > 0) {
     pool = (uint64_t)st->pool_paths;
-  } else {  // default: up to 8 Mi slots (C2 on B200: 4 Mi 48.7 ms, 8 Mi 45.9, 16 Mi 44.9), less for renders that cannot fill them
-    pool = 1u << 16;
-    while (pool < (1u << 23) && pool < want_paths) pool <<= 1;
+  } else {
+    // Default pool.  Measured on C2 (profiles/r2_pool_sweep.jsonl, tools/pool_share_probe.py): fastest when the WHOLE job is
+    // in flight at once (as many iterations as the depth limit, all of them as full as they can be: 41.6 ms against
+    // 43.2 ms at 48 Mi slots), next best with many fills of a large pool, worst when a second, ragged fill trails the
+    // first (46.6 ms at 0.8 x the job).  So: the job itself if that fits a quarter of the free memory (and 48 GiB),
+    // else 48 Mi slots, and never between one and 2.5 fills.
+    const uint64_t per_slot = 128ull + (s->mesh_objects > 0 ? 96ull : 0ull) + (nee ? 8ull : 0ull);
+    if (s->pool_budget_bytes == 0) {
+      // asked once per scene: cudaMemGetInfo contends with NVML pollers (nvidia-smi -lms) for tens of milliseconds
+      size_t free_b = 0, total_b = 0;
+      CK(cudaMemGetInfo(&free_b, &total_b));
+      s->pool_budget_bytes = std::max<uint64_t>(std::min<uint64_t>((uint64_t)free_b / 4, 48ull << 30), 1ull << 24);
+    }
+    const uint64_t budget = s->pool_budget_bytes / per_slot;
+    const uint64_t want_slots = nee ? 2 * want_paths : want_paths;  // with NEE paths may fill half a segment only
+    if (want_slots <= budget) {
+      pool = std::max<uint64_t>(want_slots, 1u << 16);
+    } else {
+      pool = std::min<uint64_t>(budget, 48ull << 20);
+      if (want_slots < 5 * pool / 2) pool = (want_slots + 2) / 3;
+    }
   }
   const uint32_t segments = s->segments();
   uint64_t cap64 = (pool + segments - 1) / segments;
@@ -266,8 +293,8 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
   if (cap64 * segments > 0x7fffffffull) throw std::invalid_argument("pool_paths too large");
   ensure_ctl(s);
   s->ws.ensure(segments, (uint32_t)cap64, s->mesh_objects, false, true);
-  const bool nee = (st->flags & PTC_FLAG_NEE) != 0;
   if (nee) s->ws.ensure_aux();
+  s->last_pool_slots = (int64_t)cap64 * segments;
   Buffers bufs[2] = {s->ws.buffers(0), s->ws.buffers(1)};
   bufs[0].cap = bufs[1].cap = (uint32_t)cap64;  // a pool smaller than the allocation simply uses a smaller segment stride
   const TaskQ tq = s->ws.taskq();
@@ -754,6 +781,8 @@ int ptc_scene_commit_ex(ptc_scene *s, int device, int flags) {
   return 0;
   PTC_GUARD_END
 }
+
+int64_t ptc_scene_last_pool_slots(const ptc_scene *s) { return s ? s->last_pool_slots : 0; }
 
 int ptc_scene_mesh_info(const ptc_scene *s, int object, ptc_mesh_info *info, uint8_t *dead, int32_t *order) {
   PTC_GUARD_BEGIN

@@ -102,6 +102,7 @@ extern "C" {
                               world_to_object: *const f32, material: c_int) -> c_int;
     pub fn ptc_scene_set_sky_hdr(s: *mut ptc_scene, rgb: *const f32, w: i32, h: i32) -> c_int;
     pub fn ptc_scene_build(s: *mut ptc_scene) -> c_int;
+    pub fn ptc_scene_last_pool_slots(s: *const ptc_scene) -> i64;
     pub fn ptc_scene_commit(s: *mut ptc_scene, device: c_int) -> c_int;
     /// flags: PTC_COMMIT_FAST_BUILD = 1 (flatten meshes entirely on the device: quick commit, slower traversal)
     pub fn ptc_scene_commit_ex(s: *mut ptc_scene, device: c_int, flags: c_int) -> c_int;
