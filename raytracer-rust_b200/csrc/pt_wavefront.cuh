@@ -769,8 +769,11 @@ __device__ __forceinline__ void pdl_prologue() {
 }
 
 // ---- per-stage kernels: one block per segment --------------------------------------------------------------------
+// `progress` (pinned host memory mapped into the device, or nullptr): one word per render the host polls instead of
+// putting a copy of the control block between the launches of every drain iteration — `seq << 2 | supply exhausted << 1 |
+// no rays left`, the state the shade of iteration seq - 1 left behind.  One 4-byte store: never seen half-written.
 __global__ void __launch_bounds__(kBlock, kSegPerSM) k_extend_pre(Ctl *ctl, SegRange sr, DScene sc, ExtendOut out, TaskQ tq, float t_min,
-                                                                  float t_max) {
+                                                                  float t_max, volatile uint32_t *progress, uint32_t seq) {
   pdl_prologue();
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // iteration bookkeeping (the previous shade has finished: stream order)
     const uint32_t live = ctl->n_live[sr.half];
@@ -779,6 +782,10 @@ __global__ void __launch_bounds__(kBlock, kSegPerSM) k_extend_pre(Ctl *ctl, SegR
       ctl->iterations[sr.half]++;
     }
     ctl->n_live[sr.half] = 0;
+    if (progress) {
+      *progress = seq << 2 | (ctl->next_path >= ctl->total_paths ? 2u : 0u) | (live == 0u ? 1u : 0u);
+      __threadfence_system();
+    }
   }
   if (sc.n_objects <= kSmemObjects) stage_pre<true>(sr.seg0 + blockIdx.x, sr.n_seg, sc, out, tq, t_min, t_max);
   else stage_pre<false>(sr.seg0 + blockIdx.x, sr.n_seg, sc, out, tq, t_min, t_max);

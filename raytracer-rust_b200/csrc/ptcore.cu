@@ -151,6 +151,7 @@ struct ptc_scene {
   DevBuf<uint32_t> w_packed;
   DevBuf<Ctl> d_ctl;
   Ctl *h_ctl = nullptr;  // pinned ring
+  uint32_t *h_progress = nullptr;  // pinned + mapped: the word k_extend_pre reports the state of the render in
   static constexpr int kRing = 4;
   cudaEvent_t ring_ev[kRing] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;  // render_ms brackets, created once (ensure_ctl)
@@ -169,6 +170,7 @@ struct ptc_scene {
     }
     if (device >= 0) cudaSetDevice(device);
     if (h_ctl) cudaFreeHost(h_ctl);
+    if (h_progress) cudaFreeHost(h_progress);
     if (h_film) cudaFreeHost(h_film);
     for (auto &e : ring_ev)
       if (e) cudaEventDestroy(e);
@@ -215,7 +217,7 @@ uint32_t traverse_refill_arg() {
 int launch_extend(cudaStream_t stream, uint32_t segments, int rounds, Ctl *ctl, const DScene &ds, const ExtendOut &eo, const TaskQ &tq,
                   float t_min, float t_max, bool counters) {
   const SegRange sr{0u, segments, 0u, 0u, 1u};
-  k_extend_pre<<<segments, kBlock, 0, stream>>>(ctl, sr, ds, eo, tq, t_min, t_max);
+  k_extend_pre<<<segments, kBlock, 0, stream>>>(ctl, sr, ds, eo, tq, t_min, t_max, nullptr, 0u);
   for (int r = 0; r < rounds; r++) {
     const SegRange tsr{0u, segments, 0u, (uint32_t)r, 1u};
     if (counters) k_traverse<true><<<segments, kBlock, 0, stream>>>(ctl, tsr, ds, tq, r, t_min, eo.b.cap, traverse_refill_arg());
@@ -234,6 +236,7 @@ void ensure_ctl(ptc_scene *s) {
   if (s->h_ctl) return;
   s->d_ctl.alloc(1);
   CK(cudaMallocHost(&s->h_ctl, sizeof(Ctl) * ptc_scene::kRing));
+  CK(cudaHostAlloc(&s->h_progress, 64, cudaHostAllocMapped | cudaHostAllocPortable));
   for (auto &e : s->ring_ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   CK(cudaEventCreate(&s->ev_begin));
   CK(cudaEventCreate(&s->ev_end));
@@ -385,10 +388,22 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
     uint32_t trav_seq = 0;
     bool draining = false;  // a snapshot has shown the path supply exhausted
     int flip = 0;  // the ray set the extend stages read
+    // How the host learns that the render is over.  Default: k_extend_pre writes one word into mapped host memory
+    // (pt_wavefront.cuh) and the host polls it — nothing sits between the launches, and the host stays at most a few
+    // iterations ahead of the device.  PTC_PROGRESS=0: round 1's way, a copy of the control block + an event in the stream
+    // (every iteration of the drain: the copy engine's turn and a launch that cannot overlap cost ~7 us of each ~55 us).
+    const bool progress_on = getenv("PTC_PROGRESS") ? atoi(getenv("PTC_PROGRESS")) != 0 : true;
+    uint32_t *d_progress = nullptr;
+    if (progress_on) {
+      CK(cudaHostGetDevicePointer((void **)&d_progress, s->h_progress, 0));
+      *(volatile uint32_t *)s->h_progress = 0u;
+    }
+    uint64_t it = 0;
     auto run_extend = [&]() {
       const ExtendOut eo{bufs[flip], nullptr};
       if (timing) mark(ST_PRE);
-      launch_stage(pdl, stream, segments, k_extend_pre, s->d_ctl.p, sr, s->ds, eo, tq, kEps, INFINITY);  // renderer.rs:24
+      launch_stage(pdl, stream, segments, k_extend_pre, s->d_ctl.p, sr, s->ds, eo, tq, kEps, INFINITY, (volatile uint32_t *)d_progress,
+                   (uint32_t)(it + 1));  // renderer.rs:24
       for (int r = 0; r < rounds; r++) {
         if (timing) mark(ST_TRAVERSE);
         const SegRange tsr{0u, segments, 0u, trav_seq++, draining ? 1u : trav_parts_bulk};
@@ -407,38 +422,74 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
       flip ^= 1;
     };
     run_shade();  // initial fill: a shade pass over empty segments is pure regeneration
-    std::deque<int> pending;
-    int ring_next = 0;
-    uint64_t it = 0;
-    int check_every = 4;  // 1 once a snapshot shows the path supply exhausted: the drain's launches are cheap, running ahead of
-                          // the device by up to kRing x 4 empty iterations at the end of every render is not
     bool finished = false;
-    while (!finished) {
-      run_extend();
-      run_shade();
-      it++;
-      if (it % check_every == 0) {
-        // snapshot the control block; consume finished snapshots without stalling the launch queue.  The host only
-        // blocks when the ring is full.
-        const int k = ring_next;
-        ring_next = (ring_next + 1) % ptc_scene::kRing;
-        CK(cudaMemcpyAsync(&s->h_ctl[k], s->d_ctl.p, sizeof(Ctl), cudaMemcpyDeviceToHost, stream));
-        CK(cudaEventRecord(s->ring_ev[k], stream));
-        pending.push_back(k);
-        while (!pending.empty()) {
-          const int o = pending.front();
-          const bool must_wait = (int)pending.size() >= ptc_scene::kRing;
-          if (!must_wait && cudaEventQuery(s->ring_ev[o]) == cudaErrorNotReady) {
-            cudaGetLastError();
-            break;
-          }
-          CK(cudaEventSynchronize(s->ring_ev[o]));
-          pending.pop_front();
-          if (is_done(s->h_ctl[o])) {
+    uint64_t last_iteration = ~0ull;
+    if (progress_on) {
+      const volatile uint32_t *prog = s->h_progress;
+      while (!finished) {
+        run_extend();
+        run_shade();
+        it++;
+        // the extend of iteration k reports what the shade of iteration k - 1 left: nothing alive and nothing to start
+        // means every launch from k on is empty.  Ahead of the device by kAhead iterations at most (4 launches of ~2.5 us
+        // each against >= 45 us per iteration: two would do), so that few empty launches trail the render.
+        // And once the supply is known to be exhausted the end is known too: a path started by the shade of iteration
+        // k - 1 at the latest has its last segment in iteration k - 1 + max_depth (the whole job in flight at once:
+        // exactly max_depth iterations, no trailing launch at all).
+        constexpr uint64_t kAhead = 3;
+        for (uint32_t spins = 0;; spins++) {
+          const uint32_t w = *prog;
+          if ((w & 3u) == 3u) {
             finished = true;
             break;
           }
-          if (s->h_ctl[o].next_path >= s->h_ctl[o].total_paths) check_every = 1, draining = true;
+          if ((w & 2u) && !draining) {
+            draining = true;
+            last_iteration = (uint64_t)(w >> 2) - 1u + (uint64_t)rp.max_depth + (nee ? 1u : 0u);  // + the last hit's shadow ray
+          }
+          if (it >= last_iteration) {
+            finished = true;
+            break;
+          }
+          if (it < kAhead + (uint64_t)(w >> 2)) break;
+          if ((spins & 0x3ffu) == 0x3ffu) {  // a device fault must not leave the host spinning
+            const cudaError_t e = cudaStreamQuery(stream);
+            if (e != cudaSuccess && e != cudaErrorNotReady) CK(e);
+          }
+        }
+      }
+    } else {
+      std::deque<int> pending;
+      int ring_next = 0;
+      int check_every = 4;  // 1 once a snapshot shows the path supply exhausted: the drain's launches are cheap, running ahead of
+                            // the device by up to kRing x 4 empty iterations at the end of every render is not
+      while (!finished) {
+        run_extend();
+        run_shade();
+        it++;
+        if (it % check_every == 0) {
+          // snapshot the control block; consume finished snapshots without stalling the launch queue.  The host only
+          // blocks when the ring is full.
+          const int k = ring_next;
+          ring_next = (ring_next + 1) % ptc_scene::kRing;
+          CK(cudaMemcpyAsync(&s->h_ctl[k], s->d_ctl.p, sizeof(Ctl), cudaMemcpyDeviceToHost, stream));
+          CK(cudaEventRecord(s->ring_ev[k], stream));
+          pending.push_back(k);
+          while (!pending.empty()) {
+            const int o = pending.front();
+            const bool must_wait = (int)pending.size() >= ptc_scene::kRing;
+            if (!must_wait && cudaEventQuery(s->ring_ev[o]) == cudaErrorNotReady) {
+              cudaGetLastError();
+              break;
+            }
+            CK(cudaEventSynchronize(s->ring_ev[o]));
+            pending.pop_front();
+            if (is_done(s->h_ctl[o])) {
+              finished = true;
+              break;
+            }
+            if (s->h_ctl[o].next_path >= s->h_ctl[o].total_paths) check_every = 1, draining = true;
+          }
         }
       }
     }

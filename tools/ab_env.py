@@ -3,7 +3,7 @@
 on one B200: a BASELINE config at its native settings and at the 1/8 sample share one of eight GPUs gets under strong
 scaling.  One JSON line per (config, share, value): best of 6 after warm-up, CUDA-event render time.
 
-  python tools/ab_env.py PTC_STEAL 1,0 C2 C5"""
+  python tools/ab_env.py PTC_STEAL 1,0 C2 C5        (AB_POOL = pool slots, default 12 Mi; 0 = the library's default)"""
 import json
 import os
 import sys
@@ -25,7 +25,7 @@ def main():
         for share in (1, 8):
             for v in values:
                 os.environ[var] = v
-                st = scene.render_settings(spp=spp, sample_begin=0, sample_end=max(1, spp // share), seed=0, pool_paths=3 << 22)
+                st = scene.render_settings(spp=spp, sample_begin=0, sample_end=max(1, spp // share), seed=0, pool_paths=int(os.environ.get("AB_POOL", str(3 << 22))))
                 best = None
                 for _ in range(6):
                     _, s = cs.render_u32(scene.camera, st)
