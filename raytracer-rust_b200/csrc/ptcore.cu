@@ -518,12 +518,17 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
       // every mark opens a stage that lasts until the next mark (the last one until the end-of-render event)
       double per[ST_COUNT] = {0, 0, 0, 0};
       uint64_t n_ext = 0;
+      // PTC_TRACE_STAGES=<file>: every launch's stage number and milliseconds, in launch order (tools/drain_trace.py)
+      const char *trace_path = getenv("PTC_TRACE_STAGES");
+      FILE *trace = trace_path ? fopen(trace_path, "w") : nullptr;
       for (size_t k = 0; k < tev_used; k++) {
         float a = 0.0f;
         CK(cudaEventElapsedTime(&a, s->timing_events[k], k + 1 < tev_used ? s->timing_events[k + 1] : ev_end));
+        if (trace) fprintf(trace, "%d %.6f\n", mark_stage[k], a);
         per[mark_stage[k]] += a;
         if (mark_stage[k] == ST_PRE) n_ext++;
       }
+      if (trace) fclose(trace);
       stats->pre_ms = per[ST_PRE];
       stats->traverse_ms = per[ST_TRAVERSE];
       stats->post_ms = per[ST_POST];

@@ -21,7 +21,7 @@ warm = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 label, scene = workloads.workload(cfg)
 cs = scene.to_core().commit(0)
 w, h, spp, depth = scene.settings
-st = scene.render_settings(spp=spp, sample_begin=0, sample_end=max(1, spp // share), seed=0, pool_paths=3 << 22)
+st = scene.render_settings(spp=spp, sample_begin=0, sample_end=max(1, spp // share), seed=0, pool_paths=int(os.environ.get("AB_POOL", str(3 << 22))))
 for _ in range(warm + 1):
     _, s = cs.render_u32(scene.camera, st)
 print(json.dumps({"config": label, "share": share, "render_ms": s.render_ms, "iterations": s.iterations, "launches": s.kernel_launches,
