@@ -15,8 +15,9 @@
 //                  block REGENERATES: tops the segment up with fresh camera paths (Philox jitter + Camera::get_ray)
 //
 // Consequences: no global compaction, no global queue cursor — the only same-address global atomics left are one
-// `next_path` reservation and one `n_live` add per block and iteration (per-warp atomics on single counters were 16-56 %
-// of the stall samples of the previous design, profiles/r1_v3_*); the ray arrays are ping-ponged between two sets (k_shade reads one, writes the other); each block's working
+// `next_path` reservation and one ray-count add per block and iteration (per-warp atomics on single counters were 16-56 %
+// of the stall samples of the previous design, profiles/r1_v3_*); a block never needs another block's data, so the
+// launches of a render are ordered per SEGMENT, not per launch (stage_begin / stage_end below); the ray arrays are ping-ponged between two sets (k_shade reads one, writes the other); each block's working
 // set stays in its own slice of memory; when the path supply runs out all segments drain together, so the tail needs
 // no repacking either.  (A persistent one-kernel variant and a two-stream variant of this loop were measured slower on
 // B200 and removed; DESIGN.md section 5 keeps the numbers.)
@@ -46,8 +47,9 @@ struct Ctl {
   unsigned long long total_paths;  // path index space of this call (padded tiles x samples)
   unsigned long long rays;         // extend items so far = trace_ray calls with depth > 0
   unsigned long long nodes, tris, mesh_rays;  // PTC_FLAG_COUNTERS
-  uint32_t n_live[2];      // rays alive after the last shade (sum of the segment counts); [0] is used
-  uint32_t iterations[2];  // [0] is used
+  uint32_t n_active;       // segments that are not yet empty for good (see stage_shade); 0 = the render is over
+  uint32_t sync_timeouts;  // stage_begin gave up waiting for a segment's previous stage (must stay 0)
+  uint32_t iterations[2];  // [0]: the last iteration that had a ray to extend
   uint32_t trav_next[8];   // k_traverse launch i hands out (segment, part) items from trav_next[i & 7] and resets entry (i + 4) & 7
 };
 
@@ -55,8 +57,14 @@ struct Ctl {
 struct SegRange {
   uint32_t seg0;   // first segment of this launch
   uint32_t n_seg;  // segments of the whole pool (stride of the task-count table)
-  uint32_t half;   // index into Ctl::n_live / iterations (always 0 today)
+  uint32_t half;   // (unused)
   uint32_t trav_seq, trav_parts;  // k_traverse only: sequence number of the launch, parts every segment's task list is cut into
+  // Segment-level ordering of the launches of a render (stage_begin / stage_end below).  flags[seg] = number of the last
+  // launch that finished this segment; flags[n_seg + seg] = 1 once the segment is empty for good.  nullptr: stream order
+  // alone (ptc_intersect).
+  uint32_t *flags;
+  uint32_t stage_id;   // number of this launch, 1, 2, 3, ... within the render
+  uint32_t flag_wait;  // 1: a block waits for ITS segment's flag to reach stage_id - 1; 0: for the whole preceding launch
 };
 
 struct RenderParams {
@@ -509,9 +517,12 @@ __device__ __forceinline__ uint32_t block_rank(bool flag, uint32_t *s_warp /* [k
 // The path count of a segment is capped at cap / 2 so that paths + their shadow rays always fit.  The estimator's
 // expectation is the plain integrator's (tested): same image, less variance where the lights are small.
 // Returns the new ray count of the segment.
+// `seg_done` (or nullptr): one word per segment, set when the segment is found empty with the path supply exhausted — it
+// will never hold a ray again — and counted off ctl->n_active, once.
+// (The path state is read with plain loads: launches overlap, see stage_begin, so it is not read-only while a k_shade runs.)
 template <bool NEE>
-__device__ __forceinline__ uint32_t stage_shade(uint32_t seg, uint32_t n_seg, uint32_t half, Ctl *ctl, const DScene &sc, const RenderParams &rp, const Buffers &b,
-                                                const Film &film) {
+__device__ __forceinline__ uint32_t stage_shade(uint32_t seg, uint32_t n_seg, uint32_t *seg_done, Ctl *ctl, const DScene &sc, const RenderParams &rp,
+                                                const Buffers &b, const Film &film) {
   __shared__ uint16_t s_perm[kShadeWindow];
   __shared__ uint32_t s_hist[2][16];
   __shared__ uint32_t s_warp[kBlock / 32 + 1];
@@ -535,9 +546,9 @@ __device__ __forceinline__ uint32_t stage_shade(uint32_t seg, uint32_t n_seg, ui
       const uint32_t idx = (uint32_t)r * kBlock + tid;
       uint32_t key = kShadeClasses - 1;
       if (idx < wn) {
-        const uint32_t bits = f2u(__ldg(&b.hit1[win_base + idx]).w);
+        const uint32_t bits = f2u(b.hit1[win_base + idx].w);
         key = (bits & kHitBit) ? 1u + ((bits >> kTypeShift) & 15u) : 0u;
-        if (NEE && (f2u(__ldg(&b.ray_o[win_base + idx].w)) & kShadowBit)) key = 9u;
+        if (NEE && (f2u(b.ray_o[win_base + idx].w) & kShadowBit)) key = 9u;
       }
       const uint32_t peers = __match_any_sync(0xffffffffu, key);
       const int leader = __ffs((int)peers) - 1;
@@ -576,8 +587,8 @@ __device__ __forceinline__ uint32_t stage_shade(uint32_t seg, uint32_t n_seg, ui
       float npdf = -1.0f;
       if (p < wn) {
         const uint32_t i = win_base + (uint32_t)s_perm[p];
-        const float4 o4 = __ldg(&b.ray_o[i]), d4 = __ldg(&b.ray_d[i]), b4 = __ldg(&b.beta[i]);
-        const float4 h1 = __ldg(&b.hit1[i]);
+        const float4 o4 = b.ray_o[i], d4 = b.ray_d[i], b4 = b.beta[i];
+        const float4 h1 = b.hit1[i];
         const uint32_t pixel_word = f2u(o4.w), sample = f2u(d4.w), bounce = f2u(b4.w);
         const uint32_t pixel = NEE ? (pixel_word & ~kShadowBit) : pixel_word;
         const uint32_t bits = f2u(h1.w);
@@ -589,12 +600,12 @@ __device__ __forceinline__ uint32_t stage_shade(uint32_t seg, uint32_t n_seg, ui
           // a shadow ray: beta is the MIS-weighted contribution, the sample field the distance to the light point.  The light
           // itself is hit at that distance; anything nearer (by more than the tolerance) occludes.
           const float t_light = d4.w;
-          if (!(bits & kHitBit) || !(__ldg(&b.hit0[i]).w < t_light * (1.0f - 2e-4f))) radiance = beta, add = true;
+          if (!(bits & kHitBit) || !(b.hit0[i].w < t_light * (1.0f - 2e-4f))) radiance = beta, add = true;
         } else if (!(bits & kHitBit)) {
           radiance = beta * sky_color(sc, ray_d);
           add = true;
         } else {
-          const float4 h0 = __ldg(&b.hit0[i]);
+          const float4 h0 = b.hit0[i];
           const DMaterial m = sc.materials[bits & kMatMask];
           const V3 pos = v3(h0.x, h0.y, h0.z), nrm = v3(h1.x, h1.y, h1.z);
           const V3 e = mat_emitted(m);
@@ -752,54 +763,101 @@ __device__ __forceinline__ uint32_t stage_shade(uint32_t seg, uint32_t n_seg, ui
   }
   if (tid == 0) {
     b.cnt[seg] = w;
-    if (w) atomicAdd(&ctl->n_live[half], w);
+    // w == 0 here means the loop above ended on an exhausted supply: the segment is empty for good
+    if (w == 0u && seg_done && seg_done[seg] == 0u) {
+      seg_done[seg] = 1u;
+      atomicSub(&ctl->n_active, 1u);
+    }
   }
   return w;
 }
 
 
-// Programmatic dependent launch (sm_90+): the host marks every stage launch of a render as allowed to start before its
-// predecessor in the stream has drained; a kernel first lets ITS successor be scheduled, then waits until the
-// predecessor has completed and its writes are visible.  What overlaps is the launch latency and block scheduling of
-// four dependent launches per iteration (~3 us each, a fifth of a drain iteration); every data access stays behind the
-// wait.  Without the launch attribute both instructions are no-ops.
-__device__ __forceinline__ void pdl_prologue() {
+// Launches as code switches, segments as the unit of ordering.
+//
+// Every stage launch of a render is a programmatic dependent launch (sm_90+): it may be scheduled before its predecessor
+// in the stream has drained.  Round 1 then waited for the whole predecessor (griddepcontrol.wait) — and so every stage of
+// every iteration ended with the GPU waiting for the one block that had drawn the longest walk: a constant 20-28 us per
+// traversal launch, ~40 us per iteration, 1.1 ms of the 6.2 ms of C2's 1/8 share (tools/drain_trace.py).  But block b of a
+// launch only ever needs what block b of the launch before it wrote: a block touches nothing outside its own segment.
+// So a block now waits for ITS segment: flags[seg] is set to the launch's number by the block that finished the segment
+// (release, after a block barrier) and awaited by the same-numbered block of the next launch (acquire, then a block
+// barrier).  A segment whose traversal was slow falls behind while the others go on into the next stages and
+// iterations, a different one is slow next time, and what is waited for is the SUM over a segment's stages, once, at the
+// end of the render — what a persistent per-block loop would give, without four stages' code fighting for one
+// instruction cache.  No deadlock: a dependent launch's blocks are scheduled only when every block of
+// the launch before it has started, so the block a waiting block depends on is always resident (or done) itself.
+// A launch without flags, or with flag_wait = 0 (the first launch after the host's memsets; a traversal whose blocks
+// take other segments' task-list parts, and the launch after it), waits for the whole predecessor as before.
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void stage_begin(const SegRange &sr, uint32_t seg, Ctl *ctl) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (sr.flags == nullptr || sr.flag_wait == 0u) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    return;
+  }
+  if (threadIdx.x == 0) {
+    const uint32_t need = sr.stage_id - 1u;
+    uint32_t spins = 0;
+    while (ld_acquire_u32(sr.flags + seg) < need) {
+      if (++spins == (1u << 25)) {  // tens of seconds: cannot happen; the host reports it instead of hanging
+        atomicAdd(&ctl->sync_timeouts, 1u);
+        break;
+      }
+    }
+  }
+  __syncthreads();
+}
+// every thread of the block has finished the segment's stage
+__device__ __forceinline__ void stage_end(const SegRange &sr, uint32_t seg) {
+  if (sr.flags == nullptr) return;
+  __syncthreads();
+  if (threadIdx.x == 0) st_release_u32(sr.flags + seg, sr.stage_id);  // release at gpu scope: cumulative over the barrier
 }
 
 // ---- per-stage kernels: one block per segment --------------------------------------------------------------------
 // `progress` (pinned host memory mapped into the device, or nullptr): one word per render the host polls instead of
 // putting a copy of the control block between the launches of every drain iteration — `seq << 2 | supply exhausted << 1 |
-// no rays left`, the state the shade of iteration seq - 1 left behind.  One 4-byte store: never seen half-written.
+// every segment empty for good`, as segment 0 finds it at the start of iteration seq.  One 4-byte store: never seen
+// half-written.
 __global__ void __launch_bounds__(kBlock, kSegPerSM) k_extend_pre(Ctl *ctl, SegRange sr, DScene sc, ExtendOut out, TaskQ tq, float t_min,
                                                                   float t_max, volatile uint32_t *progress, uint32_t seq) {
-  pdl_prologue();
-  if (blockIdx.x == 0 && threadIdx.x == 0) {  // iteration bookkeeping (the previous shade has finished: stream order)
-    const uint32_t live = ctl->n_live[sr.half];
-    if (live) {
-      atomicAdd(&ctl->rays, (unsigned long long)live);
-      ctl->iterations[sr.half]++;
+  const uint32_t seg = sr.seg0 + blockIdx.x;
+  stage_begin(sr, seg, ctl);
+  if (threadIdx.x == 0) {  // bookkeeping, per segment: rays = extend items = trace_ray calls with depth > 0
+    const uint32_t n = out.b.cnt[seg];
+    if (n) {
+      atomicAdd(&ctl->rays, (unsigned long long)n);
+      atomicMax(&ctl->iterations[0], seq);
     }
-    ctl->n_live[sr.half] = 0;
-    if (progress) {
-      *progress = seq << 2 | (ctl->next_path >= ctl->total_paths ? 2u : 0u) | (live == 0u ? 1u : 0u);
+    if (progress && blockIdx.x == 0) {
+      *progress = seq << 2 | (ctl->next_path >= ctl->total_paths ? 2u : 0u) | (ctl->n_active == 0u ? 1u : 0u);
       __threadfence_system();
     }
   }
-  if (sc.n_objects <= kSmemObjects) stage_pre<true>(sr.seg0 + blockIdx.x, sr.n_seg, sc, out, tq, t_min, t_max);
-  else stage_pre<false>(sr.seg0 + blockIdx.x, sr.n_seg, sc, out, tq, t_min, t_max);
+  if (sc.n_objects <= kSmemObjects) stage_pre<true>(seg, sr.n_seg, sc, out, tq, t_min, t_max);
+  else stage_pre<false>(seg, sr.n_seg, sc, out, tq, t_min, t_max);
+  stage_end(sr, seg);
 }
 template <bool COUNT>
 __global__ void __launch_bounds__(kBlock, kSegPerSM) k_traverse(Ctl *ctl, SegRange sr, DScene sc, TaskQ tq, int round, float t_min,
                                                                 uint32_t cap, uint32_t refill_lanes) {
-  pdl_prologue();
-  // (every launch, split or not, prepares the hand-out counter of the launch four after it: no launch nearer than +2 can be running)
-  if (blockIdx.x == 0 && threadIdx.x == 0) ctl->trav_next[(sr.trav_seq + 4u) & 7u] = gridDim.x;
+  stage_begin(sr, sr.seg0 + blockIdx.x, ctl);
   if (sr.trav_parts <= 1u) {
     stage_traverse<COUNT>(sr.seg0 + blockIdx.x, sr.n_seg, ctl, sc, tq, round, t_min, cap, refill_lanes);
+    stage_end(sr, sr.seg0 + blockIdx.x);
     return;
   }
+  // (a split launch waits for the whole launch before it and the launch after it for the whole of this one — flag_wait = 0,
+  // the host sees to it — so launches i and i + 4 never overlap; it prepares the hand-out counter of split launch i + 4)
+  if (blockIdx.x == 0 && threadIdx.x == 0) ctl->trav_next[(sr.trav_seq + 4u) & 7u] = gridDim.x;
   // Heavy meshes, bulk of the render (the host decides): every segment's task list is cut into `trav_parts` items and
   // the items beyond the first per block are handed out by a counter — a block whose walks were short takes another
   // item instead of idling until the slowest block of the launch is done (C5: 5-10 % of every traversal launch).
@@ -816,16 +874,18 @@ __global__ void __launch_bounds__(kBlock, kSegPerSM) k_traverse(Ctl *ctl, SegRan
     item = s_item;
   }
 }
-__global__ void __launch_bounds__(kBlock, kSegPerSM) k_extend_post(SegRange sr, DScene sc, ExtendOut out, TaskQ tq, int round, float t_min,
-                                                                   float t_max) {
-  pdl_prologue();
+__global__ void __launch_bounds__(kBlock, kSegPerSM) k_extend_post(Ctl *ctl, SegRange sr, DScene sc, ExtendOut out, TaskQ tq, int round,
+                                                                   float t_min, float t_max) {
+  stage_begin(sr, sr.seg0 + blockIdx.x, ctl);
   if (sc.n_objects <= kSmemObjects) stage_post<true>(sr.seg0 + blockIdx.x, sr.n_seg, sc, out, tq, round, t_min, t_max);
   else stage_post<false>(sr.seg0 + blockIdx.x, sr.n_seg, sc, out, tq, round, t_min, t_max);
+  stage_end(sr, sr.seg0 + blockIdx.x);
 }
 template <bool NEE>
 __global__ void __launch_bounds__(kBlock, kSegPerSM) k_shade(Ctl *ctl, SegRange sr, DScene sc, RenderParams rp, Buffers b, Film film) {
-  pdl_prologue();
-  stage_shade<NEE>(sr.seg0 + blockIdx.x, sr.n_seg, sr.half, ctl, sc, rp, b, film);
+  stage_begin(sr, sr.seg0 + blockIdx.x, ctl);
+  stage_shade<NEE>(sr.seg0 + blockIdx.x, sr.n_seg, sr.flags ? sr.flags + sr.n_seg : nullptr, ctl, sc, rp, b, film);
+  stage_end(sr, sr.seg0 + blockIdx.x);
 }
 
 // accum[i] += fp32(film sum i): the end of every render (ptc_render_accumulate ADDS into the caller's fp32 film)

@@ -80,6 +80,7 @@ struct Workspace {
   DevBuf<float4> ray_o2, ray_d2, beta2;  // second set of ray arrays (renders only): k_shade reads one set, writes the other
   DevBuf<float> aux, aux2;               // PTC_FLAG_NEE only (allocated at the first such render)
   DevBuf<uint32_t> cnt;
+  DevBuf<uint32_t> seg_flags;  // [2 * segments]: SegRange::flags
   DevBuf<uint2> tq_ray[2];
   DevBuf<float4> tq_o[2], tq_d[2];
   DevBuf<unsigned long long> tq_res[2];
@@ -98,6 +99,7 @@ struct Workspace {
     const size_t n = slots();
     ray_o.alloc(n), ray_d.alloc(n), beta.alloc(n), hit0.alloc(n), hit1.alloc(n);
     cnt.alloc(segments);
+    seg_flags.alloc(2 * (size_t)segments);
     if (rounds > 0) {
       for (int k = 0; k < 2; k++) tq_ray[k].alloc(n), tq_o[k].alloc(n), tq_d[k].alloc(n), tq_res[k].alloc(n);
       tq_cnt.alloc((size_t)(rounds + 1) * segments);
@@ -222,7 +224,7 @@ int launch_extend(cudaStream_t stream, uint32_t segments, int rounds, Ctl *ctl, 
     const SegRange tsr{0u, segments, 0u, (uint32_t)r, 1u};
     if (counters) k_traverse<true><<<segments, kBlock, 0, stream>>>(ctl, tsr, ds, tq, r, t_min, eo.b.cap, traverse_refill_arg());
     else k_traverse<false><<<segments, kBlock, 0, stream>>>(ctl, tsr, ds, tq, r, t_min, eo.b.cap, traverse_refill_arg());
-    k_extend_post<<<segments, kBlock, 0, stream>>>(sr, ds, eo, tq, r, t_min, t_max);
+    k_extend_post<<<segments, kBlock, 0, stream>>>(ctl, sr, ds, eo, tq, r, t_min, t_max);
   }
   return 1 + 2 * rounds;
 }
@@ -340,6 +342,7 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
   memset(&init, 0, sizeof(init));
   for (uint32_t &v : init.trav_next) v = segments;
   init.total_paths = rp.max_depth > 0 ? (unsigned long long)rp.n_my_tiles * 1024ull * (unsigned long long)rp.n_samples : 0ull;
+  init.n_active = init.total_paths != 0ull ? segments : 0u;  // every segment reports once when it is empty for good (stage_shade)
   const size_t n_px = (size_t)st->width * st->height;
   if (s->film_sum.n < n_px * 3) s->film_sum.alloc(n_px * 3);
   if (s->film_flags.n < n_px) s->film_flags.alloc(n_px);
@@ -348,6 +351,7 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
   CK(cudaMemsetAsync(film.flags, 0, n_px * sizeof(unsigned long long), stream));
   CK(cudaMemcpyAsync(s->d_ctl.p, &init, sizeof(Ctl), cudaMemcpyHostToDevice, stream));
   CK(cudaMemsetAsync(bufs[0].cnt, 0, segments * sizeof(uint32_t), stream));
+  CK(cudaMemsetAsync(s->ws.seg_flags.p, 0, 2 * (size_t)segments * sizeof(uint32_t), stream));
 
   const bool counters = (st->flags & PTC_FLAG_COUNTERS) != 0;
   const bool timing = (st->flags & PTC_FLAG_TIMING) != 0;
@@ -372,13 +376,23 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
   CK(cudaEventRecord(ev_begin, stream));
   uint64_t launches = 0;
   const uint32_t refill = traverse_refill_arg();
-  auto is_done = [](const Ctl &c) { return c.n_live[0] == 0 && c.next_path >= c.total_paths; };
+  auto is_done = [](const Ctl &c) { return c.n_active == 0 && c.sync_timeouts == 0 && c.next_path >= c.total_paths; };
   // programmatic dependent launches, unless the per-stage events are wanted (they would sit between the launches) or
   // PTC_PDL=0
   static const bool pdl_on = getenv("PTC_PDL") ? atoi(getenv("PTC_PDL")) != 0 : true;
   const bool pdl = pdl_on && !timing;
   if (init.total_paths != 0) {
-    const SegRange sr{0u, segments, 0u, 0u, 1u};
+    // Every launch gets a number; a block waits for ITS segment to have been finished by launch number - 1 instead of for
+    // the whole launch (pt_wavefront.cuh: stage_begin).  PTC_DATAFLOW=0: whole launches, as in round 1.
+    const bool dataflow = getenv("PTC_DATAFLOW") ? atoi(getenv("PTC_DATAFLOW")) != 0 : true;
+    uint32_t stage_id = 0;
+    bool prev_sets_flags = false;  // false: the launch before cannot be waited for by segment (host work, or a split traversal)
+    auto seg_range = [&](uint32_t trav_seq_, uint32_t trav_parts_) {
+      const bool split = trav_parts_ > 1u;
+      SegRange r{0u, segments, 0u, trav_seq_, trav_parts_, s->ws.seg_flags.p, ++stage_id, (dataflow && prev_sets_flags && !split) ? 1u : 0u};
+      prev_sets_flags = !split;
+      return r;
+    };
     // k_traverse cuts the task lists into parts handed out dynamically while a scene with a heavy mesh is in the bulk of
     // its render (pt_wavefront.cuh: k_traverse); in the drain the lists are too short for that.  PTC_TRAV_PARTS overrides.
     int64_t mesh_tris = 0;
@@ -402,22 +416,23 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
     auto run_extend = [&]() {
       const ExtendOut eo{bufs[flip], nullptr};
       if (timing) mark(ST_PRE);
-      launch_stage(pdl, stream, segments, k_extend_pre, s->d_ctl.p, sr, s->ds, eo, tq, kEps, INFINITY, (volatile uint32_t *)d_progress,
-                   (uint32_t)(it + 1));  // renderer.rs:24
+      launch_stage(pdl, stream, segments, k_extend_pre, s->d_ctl.p, seg_range(0u, 1u), s->ds, eo, tq, kEps, INFINITY,
+                   (volatile uint32_t *)d_progress, (uint32_t)(it + 1));  // renderer.rs:24
       for (int r = 0; r < rounds; r++) {
         if (timing) mark(ST_TRAVERSE);
-        const SegRange tsr{0u, segments, 0u, trav_seq++, draining ? 1u : trav_parts_bulk};
+        const SegRange tsr = seg_range(trav_seq++, draining ? 1u : trav_parts_bulk);
         if (counters) launch_stage(pdl, stream, segments, k_traverse<true>, s->d_ctl.p, tsr, s->ds, tq, r, kEps, eo.b.cap, refill);
         else launch_stage(pdl, stream, segments, k_traverse<false>, s->d_ctl.p, tsr, s->ds, tq, r, kEps, eo.b.cap, refill);
         if (timing) mark(ST_POST);
-        launch_stage(pdl, stream, segments, k_extend_post, sr, s->ds, eo, tq, r, kEps, INFINITY);
+        launch_stage(pdl, stream, segments, k_extend_post, s->d_ctl.p, seg_range(0u, 1u), s->ds, eo, tq, r, kEps, INFINITY);
       }
       launches += 1 + 2 * (uint64_t)rounds;
     };
     auto run_shade = [&]() {  // reads set `flip`, writes the other one, which the next extend then reads
       if (timing) mark(ST_SHADE);
-      if (nee) launch_stage(pdl, stream, segments, k_shade<true>, s->d_ctl.p, sr, s->ds, rp, bufs[flip], film);
-      else launch_stage(pdl, stream, segments, k_shade<false>, s->d_ctl.p, sr, s->ds, rp, bufs[flip], film);
+      const SegRange ssr = seg_range(0u, 1u);
+      if (nee) launch_stage(pdl, stream, segments, k_shade<true>, s->d_ctl.p, ssr, s->ds, rp, bufs[flip], film);
+      else launch_stage(pdl, stream, segments, k_shade<false>, s->d_ctl.p, ssr, s->ds, rp, bufs[flip], film);
       launches += 1;
       flip ^= 1;
     };
@@ -509,7 +524,7 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
     memset(stats, 0, sizeof(*stats));
     stats->paths = rp.max_depth > 0 ? my_pixels * (uint64_t)rp.n_samples : 0;
     stats->rays = fin.rays;
-    stats->iterations = fin.iterations[0];
+    stats->iterations = fin.iterations[0];  // the last iteration any segment had a ray in
     stats->kernel_launches = launches;
     float ms = 0.0f;
     CK(cudaEventElapsedTime(&ms, ev_begin, ev_end));
