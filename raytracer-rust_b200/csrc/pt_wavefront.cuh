@@ -50,7 +50,6 @@ struct Ctl {
   uint32_t n_active;       // segments that are not yet empty for good (see stage_shade); 0 = the render is over
   uint32_t sync_timeouts;  // stage_begin gave up waiting for a segment's previous stage (must stay 0)
   uint32_t iterations[2];  // [0]: the last iteration that had a ray to extend
-  uint32_t trav_next[8];   // k_traverse launch i hands out (segment, part) items from trav_next[i & 7] and resets entry (i + 4) & 7
 };
 
 // A kernel launch covers segments [seg0, seg0 + gridDim.x).
@@ -60,11 +59,14 @@ struct SegRange {
   uint32_t half;   // (unused)
   uint32_t trav_seq, trav_parts;  // k_traverse only: sequence number of the launch, parts every segment's task list is cut into
   // Segment-level ordering of the launches of a render (stage_begin / stage_end below).  flags[seg] = number of the last
-  // launch that finished this segment; flags[n_seg + seg] = 1 once the segment is empty for good.  nullptr: stream order
-  // alone (ptc_intersect).
+  // launch that finished this segment; flags[n_seg + seg] = 1 once the segment is empty for good; [2 * n_seg + seg]: see
+  // trav_counter.  nullptr: stream order alone (ptc_intersect).
   uint32_t *flags;
   uint32_t stage_id;   // number of this launch, 1, 2, 3, ... within the render
   uint32_t flag_wait;  // 1: a block waits for ITS segment's flag to reach stage_id - 1; 0: for the whole preceding launch
+  // k_traverse with trav_parts > 1 only: this launch's own hand-out counter (zeroed by the host before the render; a
+  // counter per launch, so that launches far apart may overlap); flags[2 * n_seg + seg] counts the finished parts of a segment
+  uint32_t *trav_counter;
 };
 
 struct RenderParams {
@@ -787,8 +789,9 @@ __device__ __forceinline__ uint32_t stage_shade(uint32_t seg, uint32_t n_seg, ui
 // end of the render — what a persistent per-block loop would give, without four stages' code fighting for one
 // instruction cache.  No deadlock: a dependent launch's blocks are scheduled only when every block of
 // the launch before it has started, so the block a waiting block depends on is always resident (or done) itself.
-// A launch without flags, or with flag_wait = 0 (the first launch after the host's memsets; a traversal whose blocks
-// take other segments' task-list parts, and the launch after it), waits for the whole predecessor as before.
+// A traversal whose blocks take (segment, part) items from a counter waits per ITEM and counts a segment's finished
+// parts; the block that finishes the last one sets the flag.  A launch without flags, or with flag_wait = 0 (the first
+// launch after the host's memsets), waits for the whole predecessor as before.
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
   uint32_t v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -797,12 +800,9 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
 __device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ void stage_begin(const SegRange &sr, uint32_t seg, Ctl *ctl) {
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  if (sr.flags == nullptr || sr.flag_wait == 0u) {
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    return;
-  }
+// the block waits until the launch before this one has finished segment `seg` (no-op without flags / with flag_wait = 0)
+__device__ __forceinline__ void segment_wait(const SegRange &sr, uint32_t seg, Ctl *ctl) {
+  if (sr.flags == nullptr || sr.flag_wait == 0u) return;
   if (threadIdx.x == 0) {
     const uint32_t need = sr.stage_id - 1u;
     uint32_t spins = 0;
@@ -814,6 +814,11 @@ __device__ __forceinline__ void stage_begin(const SegRange &sr, uint32_t seg, Ct
     }
   }
   __syncthreads();
+}
+__device__ __forceinline__ void stage_begin(const SegRange &sr, uint32_t seg, Ctl *ctl) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (sr.flags == nullptr || sr.flag_wait == 0u) asm volatile("griddepcontrol.wait;" ::: "memory");
+  else segment_wait(sr, seg, ctl);
 }
 // every thread of the block has finished the segment's stage
 __device__ __forceinline__ void stage_end(const SegRange &sr, uint32_t seg) {
@@ -849,29 +854,42 @@ __global__ void __launch_bounds__(kBlock, kSegPerSM) k_extend_pre(Ctl *ctl, SegR
 template <bool COUNT>
 __global__ void __launch_bounds__(kBlock, kSegPerSM) k_traverse(Ctl *ctl, SegRange sr, DScene sc, TaskQ tq, int round, float t_min,
                                                                 uint32_t cap, uint32_t refill_lanes) {
-  stage_begin(sr, sr.seg0 + blockIdx.x, ctl);
   if (sr.trav_parts <= 1u) {
+    stage_begin(sr, sr.seg0 + blockIdx.x, ctl);
     stage_traverse<COUNT>(sr.seg0 + blockIdx.x, sr.n_seg, ctl, sc, tq, round, t_min, cap, refill_lanes);
     stage_end(sr, sr.seg0 + blockIdx.x);
     return;
   }
-  // (a split launch waits for the whole launch before it and the launch after it for the whole of this one — flag_wait = 0,
-  // the host sees to it — so launches i and i + 4 never overlap; it prepares the hand-out counter of split launch i + 4)
-  if (blockIdx.x == 0 && threadIdx.x == 0) ctl->trav_next[(sr.trav_seq + 4u) & 7u] = gridDim.x;
   // Heavy meshes, bulk of the render (the host decides): every segment's task list is cut into `trav_parts` items and
   // the items beyond the first per block are handed out by a counter — a block whose walks were short takes another
   // item instead of idling until the slowest block of the launch is done (C5: 5-10 % of every traversal launch).
   // Ownership of the SEGMENT is irrelevant here: a traversal only reads its task and lowers that task's result key.
-  __shared__ uint32_t s_item;
-  uint32_t *next = &ctl->trav_next[sr.trav_seq & 7u];
-  const uint32_t n_items = sr.n_seg * sr.trav_parts;
-  uint32_t item = blockIdx.x;
-  while (item < n_items) {
-    stage_traverse<COUNT>(sr.seg0 + item % sr.n_seg, sr.n_seg, ctl, sc, tq, round, t_min, cap, refill_lanes, item / sr.n_seg, sr.trav_parts);
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (sr.flags == nullptr || sr.flag_wait == 0u) asm volatile("griddepcontrol.wait;" ::: "memory");
+  __shared__ uint32_t s_item;  // the item in hand lives in shared memory: nothing of the hand-out stays in registers during a walk
+  if (threadIdx.x == 0) s_item = blockIdx.x;
+  __syncthreads();
+  for (;;) {
+    {
+      const uint32_t item = s_item;
+      if (item >= sr.n_seg * sr.trav_parts) break;
+      const uint32_t seg = sr.seg0 + item % sr.n_seg;
+      segment_wait(sr, seg, ctl);
+      stage_traverse<COUNT>(seg, sr.n_seg, ctl, sc, tq, round, t_min, cap, refill_lanes, item / sr.n_seg, sr.trav_parts);
+    }
     __syncthreads();
-    if (threadIdx.x == 0) s_item = atomicAdd(next, 1u);
+    if (threadIdx.x == 0) {
+      if (sr.flags) {  // the last part of a segment to finish publishes the segment (the results are L2 atomics; fenced anyway)
+        const uint32_t seg = sr.seg0 + s_item % sr.n_seg;
+        __threadfence();
+        if (atomicInc(sr.flags + 2u * sr.n_seg + seg, sr.trav_parts - 1u) == sr.trav_parts - 1u) {
+          __threadfence();
+          st_release_u32(sr.flags + seg, sr.stage_id);
+        }
+      }
+      s_item = gridDim.x + atomicAdd(sr.trav_counter, 1u);
+    }
     __syncthreads();
-    item = s_item;
   }
 }
 __global__ void __launch_bounds__(kBlock, kSegPerSM) k_extend_post(Ctl *ctl, SegRange sr, DScene sc, ExtendOut out, TaskQ tq, int round,

@@ -34,6 +34,7 @@ using namespace pt;
 using namespace ptw;
 
 namespace {
+constexpr uint32_t kTravCounters = 1u << 16;  // hand-out counters of split traversal launches, one per launch of a render
 
 thread_local std::string g_err;
 
@@ -80,7 +81,8 @@ struct Workspace {
   DevBuf<float4> ray_o2, ray_d2, beta2;  // second set of ray arrays (renders only): k_shade reads one set, writes the other
   DevBuf<float> aux, aux2;               // PTC_FLAG_NEE only (allocated at the first such render)
   DevBuf<uint32_t> cnt;
-  DevBuf<uint32_t> seg_flags;  // [2 * segments]: SegRange::flags
+  DevBuf<uint32_t> seg_flags;      // [3 * segments]: SegRange::flags
+  DevBuf<uint32_t> trav_counters;  // [kTravCounters]: SegRange::trav_counter of the render's split traversal launches
   DevBuf<uint2> tq_ray[2];
   DevBuf<float4> tq_o[2], tq_d[2];
   DevBuf<unsigned long long> tq_res[2];
@@ -99,7 +101,8 @@ struct Workspace {
     const size_t n = slots();
     ray_o.alloc(n), ray_d.alloc(n), beta.alloc(n), hit0.alloc(n), hit1.alloc(n);
     cnt.alloc(segments);
-    seg_flags.alloc(2 * (size_t)segments);
+    seg_flags.alloc(3 * (size_t)segments);
+    trav_counters.alloc(kTravCounters);
     if (rounds > 0) {
       for (int k = 0; k < 2; k++) tq_ray[k].alloc(n), tq_o[k].alloc(n), tq_d[k].alloc(n), tq_res[k].alloc(n);
       tq_cnt.alloc((size_t)(rounds + 1) * segments);
@@ -340,7 +343,6 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
 
   Ctl init;
   memset(&init, 0, sizeof(init));
-  for (uint32_t &v : init.trav_next) v = segments;
   init.total_paths = rp.max_depth > 0 ? (unsigned long long)rp.n_my_tiles * 1024ull * (unsigned long long)rp.n_samples : 0ull;
   init.n_active = init.total_paths != 0ull ? segments : 0u;  // every segment reports once when it is empty for good (stage_shade)
   const size_t n_px = (size_t)st->width * st->height;
@@ -351,7 +353,8 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
   CK(cudaMemsetAsync(film.flags, 0, n_px * sizeof(unsigned long long), stream));
   CK(cudaMemcpyAsync(s->d_ctl.p, &init, sizeof(Ctl), cudaMemcpyHostToDevice, stream));
   CK(cudaMemsetAsync(bufs[0].cnt, 0, segments * sizeof(uint32_t), stream));
-  CK(cudaMemsetAsync(s->ws.seg_flags.p, 0, 2 * (size_t)segments * sizeof(uint32_t), stream));
+  CK(cudaMemsetAsync(s->ws.seg_flags.p, 0, 3 * (size_t)segments * sizeof(uint32_t), stream));
+  CK(cudaMemsetAsync(s->ws.trav_counters.p, 0, kTravCounters * sizeof(uint32_t), stream));
 
   const bool counters = (st->flags & PTC_FLAG_COUNTERS) != 0;
   const bool timing = (st->flags & PTC_FLAG_TIMING) != 0;
@@ -386,11 +389,10 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
     // the whole launch (pt_wavefront.cuh: stage_begin).  PTC_DATAFLOW=0: whole launches, as in round 1.
     const bool dataflow = getenv("PTC_DATAFLOW") ? atoi(getenv("PTC_DATAFLOW")) != 0 : true;
     uint32_t stage_id = 0;
-    bool prev_sets_flags = false;  // false: the launch before cannot be waited for by segment (host work, or a split traversal)
     auto seg_range = [&](uint32_t trav_seq_, uint32_t trav_parts_) {
-      const bool split = trav_parts_ > 1u;
-      SegRange r{0u, segments, 0u, trav_seq_, trav_parts_, s->ws.seg_flags.p, ++stage_id, (dataflow && prev_sets_flags && !split) ? 1u : 0u};
-      prev_sets_flags = !split;
+      // (the first launch follows the host's memsets: it waits for the stream, not for a flag)
+      SegRange r{0u, segments, 0u, trav_seq_, trav_parts_, s->ws.seg_flags.p, ++stage_id, (dataflow && stage_id > 1u) ? 1u : 0u, nullptr};
+      if (trav_parts_ > 1u) r.trav_counter = s->ws.trav_counters.p + trav_seq_;
       return r;
     };
     // k_traverse cuts the task lists into parts handed out dynamically while a scene with a heavy mesh is in the bulk of
@@ -420,7 +422,9 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
                    (volatile uint32_t *)d_progress, (uint32_t)(it + 1));  // renderer.rs:24
       for (int r = 0; r < rounds; r++) {
         if (timing) mark(ST_TRAVERSE);
-        const SegRange tsr = seg_range(trav_seq++, draining ? 1u : trav_parts_bulk);
+        // (a split launch needs a hand-out counter of its own; a render with more launches than counters goes on unsplit)
+        const SegRange tsr = seg_range(trav_seq, (draining || trav_seq >= kTravCounters) ? 1u : trav_parts_bulk);
+        trav_seq++;
         if (counters) launch_stage(pdl, stream, segments, k_traverse<true>, s->d_ctl.p, tsr, s->ds, tq, r, kEps, eo.b.cap, refill);
         else launch_stage(pdl, stream, segments, k_traverse<false>, s->d_ctl.p, tsr, s->ds, tq, r, kEps, eo.b.cap, refill);
         if (timing) mark(ST_POST);
@@ -989,7 +993,6 @@ int ptc_intersect(ptc_scene *s, const float *origins, const float *dirs, int64_t
   d_out.alloc((size_t)n);
   Ctl init;
   memset(&init, 0, sizeof(init));
-  for (uint32_t &v : init.trav_next) v = segments;
   ctl.upload(&init, 1);
   cudaStream_t st = s->own_stream;
   const unsigned nb = (unsigned)((n + 255) / 256);
