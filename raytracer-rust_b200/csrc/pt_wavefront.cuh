@@ -787,7 +787,7 @@ __device__ __forceinline__ uint32_t stage_shade(uint32_t seg, uint32_t n_seg, ui
 // barrier).  A segment whose traversal was slow falls behind while the others go on into the next stages and
 // iterations, a different one is slow next time, and what is waited for is the SUM over a segment's stages, once, at the
 // end of the render — what a persistent per-block loop would give, without four stages' code fighting for one
-// instruction cache (DESIGN.md 5b).  No deadlock: a dependent launch's blocks are scheduled only when every block of
+// instruction cache (DESIGN.md 5c).  No deadlock: a dependent launch's blocks are scheduled only when every block of
 // the launch before it has started, so the block a waiting block depends on is always resident (or done) itself.
 // A traversal whose blocks take (segment, part) items from a counter waits per ITEM and counts a segment's finished
 // parts; the block that finishes the last one sets the flag.  A launch without flags, or with flag_wait = 0 (the first

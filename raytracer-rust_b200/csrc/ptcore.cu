@@ -455,7 +455,7 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
         // And once the supply is known to be exhausted the end is known too: a path started by the shade of iteration
         // k - 1 at the latest has its last segment in iteration k - 1 + max_depth (the whole job in flight at once:
         // exactly max_depth iterations, no trailing launch at all).
-        constexpr uint64_t kAhead = 3;
+        const uint64_t kAhead = getenv("PTC_AHEAD") ? (uint64_t)std::max(1, atoi(getenv("PTC_AHEAD"))) : 3u;
         for (uint32_t spins = 0;; spins++) {
           const uint32_t w = *prog;
           if ((w & 3u) == 3u) {
