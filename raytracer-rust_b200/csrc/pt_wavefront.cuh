@@ -783,8 +783,8 @@ __device__ __forceinline__ uint32_t stage_shade(uint32_t seg, uint32_t n_seg, ui
 // traversal launch, ~40 us per iteration, 1.1 ms of the 6.2 ms of C2's 1/8 share (tools/drain_trace.py).  But block b of a
 // launch only ever needs what block b of the launch before it wrote: a block touches nothing outside its own segment.
 // So a block now waits for ITS segment: flags[seg] is set to the launch's number by the block that finished the segment
-// (release, after a block barrier) and awaited by the same-numbered block of the next launch (acquire, then a block
-// barrier).  A segment whose traversal was slow falls behind while the others go on into the next stages and
+// (release, after a block barrier) and awaited by the same-numbered block of the next launch (relaxed polling, one acquire
+// fence, then a block barrier).  A segment whose traversal was slow falls behind while the others go on into the next stages and
 // iterations, a different one is slow next time, and what is waited for is the SUM over a segment's stages, once, at the
 // end of the render — what a persistent per-block loop would give, without four stages' code fighting for one
 // instruction cache.  No deadlock: a dependent launch's blocks are scheduled only when every block of
@@ -792,11 +792,15 @@ __device__ __forceinline__ uint32_t stage_shade(uint32_t seg, uint32_t n_seg, ui
 // A traversal whose blocks take (segment, part) items from a counter waits per ITEM and counts a segment's finished
 // parts; the block that finishes the last one sets the flag.  A launch without flags, or with flag_wait = 0 (the first
 // launch after the host's memsets), waits for the whole predecessor as before.
-__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
+// Polling is RELAXED (coherent at gpu scope, i.e. served by L2) and the acquire is one fence after the flag has been seen:
+// ld.acquire compiles to the load plus CCTL.IVALL, and a block spinning on that would wipe the L1 of its SM — the L1 the
+// blocks it is waiting for, two slots over, are walking their BVH out of — a million times a second.
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p) {
   uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void fence_acquire() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -806,12 +810,14 @@ __device__ __forceinline__ void segment_wait(const SegRange &sr, uint32_t seg, C
   if (threadIdx.x == 0) {
     const uint32_t need = sr.stage_id - 1u;
     uint32_t spins = 0;
-    while (ld_acquire_u32(sr.flags + seg) < need) {
+    while (ld_relaxed_u32(sr.flags + seg) < need) {
       if (++spins == (1u << 25)) {  // tens of seconds: cannot happen; the host reports it instead of hanging
         atomicAdd(&ctl->sync_timeouts, 1u);
         break;
       }
+      __nanosleep(64);
     }
+    fence_acquire();
   }
   __syncthreads();
 }
