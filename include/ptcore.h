@@ -107,7 +107,7 @@ typedef struct ptc_hit {
 typedef struct ptc_stats {
   uint64_t paths;          /* camera paths started */
   uint64_t rays;           /* extend-queue items = trace_ray calls with depth > 0 */
-  uint64_t iterations;     /* wavefront iterations */
+  uint64_t iterations;     /* wavefront iterations: the last one in which any pool segment had a ray to extend */
   uint64_t kernel_launches;
   double render_ms;        /* CUDA-event time of the whole render on the render stream */
   double extend_ms;        /* sum of CUDA-event times of the extend kernel launches (PTC_FLAG_TIMING) */

@@ -4,8 +4,9 @@
 // Replaces the body of render_scene (src/renderer.rs:87-106 of the reference) and everything trace_ray
 // (renderer.rs:19-65) calls.  One iteration of the wavefront = k_extend_pre, then (k_traverse, k_extend_post) once per
 // mesh object a ray can meet, then k_shade (which also regenerates paths).  Every launch is `segments` blocks of 256
-// threads, one block per pool segment, all sizes read on the device — the host enqueues iterations without
-// synchronising and polls a pinned snapshot of the control block every few iterations.
+// threads, one block per pool segment, all sizes read on the device, and block b of a launch waits for block b of the
+// launch before it, not for the whole launch (pt_wavefront.cuh: stage_begin) — the host enqueues iterations without
+// synchronising and reads the state of the render from a word the device writes into mapped host memory.
 //
 // There is no CPU fallback in this library: without a CUDA device commit / render / intersect return PTC_E_CUDA.
 #include <cuda_runtime.h>
