@@ -355,7 +355,6 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
   CK(cudaMemcpyAsync(s->d_ctl.p, &init, sizeof(Ctl), cudaMemcpyHostToDevice, stream));
   CK(cudaMemsetAsync(bufs[0].cnt, 0, segments * sizeof(uint32_t), stream));
   CK(cudaMemsetAsync(s->ws.seg_flags.p, 0, 3 * (size_t)segments * sizeof(uint32_t), stream));
-  CK(cudaMemsetAsync(s->ws.trav_counters.p, 0, kTravCounters * sizeof(uint32_t), stream));
 
   const bool counters = (st->flags & PTC_FLAG_COUNTERS) != 0;
   const bool timing = (st->flags & PTC_FLAG_TIMING) != 0;
@@ -402,8 +401,9 @@ void render_accumulate(ptc_scene *s, const ptc_camera *cam, const ptc_render_set
     for (const auto &mb : s->hs.meshes) mesh_tris += mb->n;
     const char *tp_env = getenv("PTC_TRAV_PARTS");
     const uint32_t trav_parts_bulk = tp_env ? (uint32_t)std::max(1, atoi(tp_env)) : (mesh_tris >= kHeavyMeshTriangles ? (uint32_t)kTravParts : 1u);
+    if (trav_parts_bulk > 1u) CK(cudaMemsetAsync(s->ws.trav_counters.p, 0, kTravCounters * sizeof(uint32_t), stream));  // before any launch
     uint32_t trav_seq = 0;
-    bool draining = false;  // a snapshot has shown the path supply exhausted
+    bool draining = false;  // the progress word (or a snapshot) has shown the path supply exhausted
     int flip = 0;  // the ray set the extend stages read
     // How the host learns that the render is over.  Default: k_extend_pre writes one word into mapped host memory
     // (pt_wavefront.cuh) and the host polls it — nothing sits between the launches, and the host stays at most a few
