@@ -95,6 +95,28 @@ def test_work_stealing_does_not_change_the_result(pt, monkeypatch):
     assert ha.tobytes() == hb.tobytes()
 
 
+def test_segment_ordering_does_not_change_the_result(pt, monkeypatch):
+    # the launches of a render are ordered per SEGMENT (a block waits for its own segment's flag), and a
+    # traversal launch may hand (segment, part) items to whichever block is free; PTC_DATAFLOW=0 goes back to whole-launch
+    # waits, PTC_TRAV_PARTS forces / forbids the split.  Paths are keyed by (pixel, sample) and the film is fixed-point, so
+    # image, ray count and iteration count must be the same in all four combinations — with the whole job in flight and
+    # with the smallest pool (hundreds of refills: the split path runs for most of the render)
+    s = pt.load_scene_from_json(os.path.join(SCENES, "semesterbild.json"))
+    cs = s.to_core().commit(0)
+    for extra in ({}, {"pool_paths": 592 * 256}):
+        kw = dict(width=200, height=150, spp=8, max_depth=30, seed=12, **extra)
+        ref, sref = cs.render(s.camera, s.render_settings(**kw))
+        assert sref.paths == 200 * 150 * 8
+        for dataflow, parts in (("0", "1"), ("1", "4"), ("0", "4"), ("1", "1")):
+            monkeypatch.setenv("PTC_DATAFLOW", dataflow)
+            monkeypatch.setenv("PTC_TRAV_PARTS", parts)
+            img, st = cs.render(s.camera, s.render_settings(**kw))
+            assert (st.rays, st.paths, st.iterations) == (sref.rays, sref.paths, sref.iterations)
+            assert np.array_equal(img, ref)
+        monkeypatch.delenv("PTC_DATAFLOW")
+        monkeypatch.delenv("PTC_TRAV_PARTS")
+
+
 def test_render_is_ordered_on_the_callers_stream(pt):
     # ptc_render_accumulate with the NULL (legacy default) stream: work queued there beforehand — a long kernel, then the
     # zeroing of the film — must be ordered before the render's film updates (the render used to run on a
