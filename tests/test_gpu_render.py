@@ -100,7 +100,8 @@ def test_segment_ordering_does_not_change_the_result(pt, monkeypatch):
     # traversal launch may hand (segment, part) items to whichever block is free; PTC_DATAFLOW=0 goes back to whole-launch
     # waits, PTC_TRAV_PARTS forces / forbids the split.  Paths are keyed by (pixel, sample) and the film is fixed-point, so
     # image, ray count and iteration count must be the same in all four combinations — with the whole job in flight and
-    # with the smallest pool (hundreds of refills: the split path runs for most of the render)
+    # with the smallest pool (smaller than the job: segments are topped up over several iterations, the split path runs
+    # until the supply is exhausted)
     s = pt.load_scene_from_json(os.path.join(SCENES, "semesterbild.json"))
     cs = s.to_core().commit(0)
     for extra in ({}, {"pool_paths": 592 * 256}):
