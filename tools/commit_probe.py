@@ -1,3 +1,9 @@
+#!/usr/bin/env python3
+"""Commit time of the 2 M-triangle mesh (config C5) on one B200, four times in a row: `device` (everything on the GPU,
+PTC_COMMIT_FAST_BUILD), `host`, or `hybrid` (the default of ptc_scene_commit: reference-BVH restatement on the device, SAH +
+collapse on the host).  PTC_BUILD_TIMING prints the builders' phase times on stderr.
+
+  python tools/commit_probe.py [device|host|hybrid]"""
 import os, sys, time
 sys.path.insert(0, os.getcwd())
 import ptload

@@ -1,3 +1,7 @@
+#!/usr/bin/env python3
+"""C2 at its native settings and at the 1/8 sample share for a range of pool sizes (16 … 160 Mi slots): where the default
+pool policy of the library (whole job in flight, or 48 Mi, never 1–2.5 fills) comes from.
+One JSON line per (share, pool)."""
 import os, sys, json
 sys.path.insert(0, os.getcwd())
 import ptload
