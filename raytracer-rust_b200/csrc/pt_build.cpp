@@ -845,7 +845,7 @@ void build_mesh(MeshBuild &m, int threads) {
       for (int s8 = 0; s8 < 8; s8++) {
         const uint32_t meta = (w[s8 >> 2] >> (8 * (s8 & 3))) & 0xffu;
         if (meta == 0) continue;
-        if ((meta & 0x30u) == 0x20u && (meta & 0x1fu) >= 24) inner++;
+        if ((meta >> 5) == 1u && (meta & 0x1fu) >= 24u) inner++;  // inner child: unary count 001, slot index + 24 (pt_bvh8.h)
         else leaf++, tris += (meta >> 5) == 1 ? 1 : ((meta >> 5) == 3 ? 2 : 3);
       }
     }
