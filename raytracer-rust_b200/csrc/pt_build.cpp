@@ -554,16 +554,26 @@ void collapse(const std::vector<B2> &b2, int32_t root, const int32_t *prim, cons
     int slot_child[8];   // ... and by slot
     uint32_t child_base, tri_base;
   };
-  std::vector<Item> queue;
   std::vector<Rec> recs;
   m.nodes.clear();
   m.tri48.clear();
   size_t n_nodes = 1, n_tris = 0;
-  queue.push_back({root, 0, 0});
   m.wide_depth = 0;
-  for (size_t qi = 0; qi < queue.size(); qi++) {
-    const Item it = queue[qi];
-    m.wide_depth = std::max(m.wide_depth, it.depth);
+  // Breadth-first, one wide LEVEL at a time (the tree is ~7 levels deep).  Finding a node's children means chasing the
+  // plan through a dozen binary nodes scattered over 100 MB — a DRAM miss each, 60 % of this step when one thread did it
+  // for all nodes — and is independent per node: every level does that part in parallel and keeps what the numbering
+  // needs (which children are leaves, how many triangles each holds).  The numbering itself — a node's inner children
+  // consecutive (provisionally in CHILD order; the slot order the traversal needs comes from the geometry and is fixed up
+  // in parallel below), a node's leaf triangles consecutive — is then a sequential pass over compact records: the same
+  // numbers as one queue would give.
+  struct Found {
+    int32_t count[8];
+    uint8_t leaf;  // bit i: child i is a leaf
+  };
+  std::vector<Item> level, next_level;
+  std::vector<Found> found;
+  level.push_back({root, 0, 0});
+  auto find_children = [&](const Item &it, Rec &rec, Found &f) {
     const B2 &n = b2[it.b2];
     int32_t ch[8];
     int nch = 0;
@@ -593,20 +603,44 @@ void collapse(const std::vector<B2> &b2, int32_t root, const int32_t *prim, cons
       ch[pick] = b2[p].left;
       ch[nch++] = b2[p].right;
     }
-    // structure only (sequential, cheap): breadth-first numbering, a node's inner children consecutive (provisionally in
-    // CHILD order; the slot order the traversal needs comes from the geometry and is fixed up in parallel below), a
-    // node's leaf triangles consecutive
-    Rec rec;
     rec.b2 = it.b2, rec.wide = it.wide, rec.nch = nch;
-    rec.child_base = (uint32_t)n_nodes, rec.tri_base = (uint32_t)n_tris;
-    for (int i = 0; i < 8; i++) rec.ch[i] = i < nch ? ch[i] : -1, rec.slot_child[i] = -1;
-    for (int i = 0; i < nch; i++) {
-      if (!is_leaf(ch[i])) queue.push_back({ch[i], (int32_t)n_nodes++, it.depth + 1});
-      else n_tris += (size_t)b2[ch[i]].count;
+    f.leaf = 0;
+    for (int i = 0; i < 8; i++) rec.ch[i] = i < nch ? ch[i] : -1, rec.slot_child[i] = -1, f.count[i] = 0;
+    for (int i = 0; i < nch; i++)
+      if (is_leaf(ch[i])) f.leaf |= (uint8_t)(1u << i), f.count[i] = b2[ch[i]].count;
+  };
+  for (int32_t depth = 0; !level.empty(); depth++) {
+    m.wide_depth = std::max(m.wide_depth, depth);
+    const size_t base = recs.size(), n_level = level.size();
+    recs.resize(base + n_level);
+    found.resize(n_level);
+    const int workers = n_level > 2048 ? (int)std::min<size_t>(16, std::max(1u, std::thread::hardware_concurrency())) : 1;
+    if (workers == 1) {
+      for (size_t i = 0; i < n_level; i++) find_children(level[i], recs[base + i], found[i]);
+    } else {
+      std::vector<std::thread> th;
+      const size_t per = (n_level + (size_t)workers - 1) / (size_t)workers;
+      for (int w = 0; w < workers; w++) {
+        const size_t lo = (size_t)w * per, hi = std::min(n_level, lo + per);
+        if (lo < hi)
+          th.emplace_back([&, lo, hi]() {
+            for (size_t i = lo; i < hi; i++) find_children(level[i], recs[base + i], found[i]);
+          });
+      }
+      for (auto &t : th) t.join();
     }
-    recs.push_back(rec);
+    next_level.clear();
+    for (size_t i = 0; i < n_level; i++) {
+      Rec &rec = recs[base + i];
+      rec.child_base = (uint32_t)n_nodes, rec.tri_base = (uint32_t)n_tris;
+      for (int c = 0; c < rec.nch; c++) {
+        if (!(found[i].leaf >> c & 1u)) next_level.push_back({rec.ch[c], (int32_t)n_nodes++, depth + 1});
+        else n_tris += (size_t)found[i].count[c];
+      }
+    }
+    level.swap(next_level);
   }
-  // queue[k].wide == k for every k (breadth-first numbering), so recs[k] describes provisional node k
+  // recs[k].wide == k for every k (breadth-first numbering): recs[k] describes provisional node k
   std::vector<uint32_t> final_of(n_nodes, 0u);
   auto assign_slots = [&](Rec &rc) {
     const B2 &n = b2[rc.b2];
